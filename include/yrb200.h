@@ -1,0 +1,175 @@
+/* yrb200.h — C ABI of the B200-native dense-retrieval backend for Youtu-RAG.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: its
+ * vector-store interface is the Python ABC `BaseVectorStore` (utu/rag/base.py:187-232) and the
+ * arithmetic sits one call below it, in chromadb's `collection.query`
+ * (utu/rag/storage/implementations/chroma_store.py:118-120).  Each entry point here names the
+ * reference call it stands in for; the Python subclass that binds them with ctypes is
+ * youtu-rag_b200/store.py (INTEGRATION.md shows the stub a maintainer adds to the reference).
+ *
+ * Conventions: plain C types only; every function returns YRB_OK (0) or a negative error code
+ * and never throws; `yrb_last_error()` gives the message for the calling thread; the library
+ * owns all device memory; callers own every host buffer; `stream` arguments are `cudaStream_t`
+ * passed as `void*` (NULL = the index's own stream).  Functions taking host buffers are
+ * synchronous; `_device` variants are asynchronous on `stream`.
+ */
+#ifndef YRB200_H
+#define YRB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YRB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define YRB_API __attribute__((visibility("default")))
+#else
+#define YRB_API
+#endif
+
+/* status codes */
+#define YRB_OK 0
+#define YRB_ERR_INVALID (-1)   /* bad argument (message says which) */
+#define YRB_ERR_CUDA (-2)      /* a CUDA runtime/driver call failed */
+#define YRB_ERR_NOMEM (-3)     /* device or host allocation failed */
+#define YRB_ERR_UNSUPPORTED (-4)
+#define YRB_ERR_NODEVICE (-5)  /* no sm_100 device visible: the product has no CPU fallback */
+
+/* distance_metric of VectorStoreConfig (utu/rag/config.py:62) → chroma hnsw:space
+ * (chroma_store.py:46-59).  score returned = 1 - distance for every metric (chroma_store.py:132-135):
+ * cosine → cos-sim, dot → inner product, euclidean → 1 - ||a-b||^2. */
+#define YRB_METRIC_COSINE 0
+#define YRB_METRIC_DOT 1
+#define YRB_METRIC_L2 2
+
+#define YRB_DTYPE_BF16 0
+#define YRB_DTYPE_F32 1
+
+/* largest k the fused (in-register / in-epilogue) selection handles; larger k takes the
+ * score-matrix + radix-select path (same results). */
+#define YRB_FUSED_K_MAX 128
+
+typedef struct yrb_index yrb_index; /* one collection's rows resident on one GPU */
+
+YRB_API int yrb_abi_version(void);
+YRB_API const char* yrb_last_error(void);
+/* number of CUDA devices with compute capability 10.x; YRB_ERR_NODEVICE if none. */
+YRB_API int yrb_device_count(int* out_count);
+
+/* ------------------------------------------------------------------ residency
+ * stands in for chromadb.PersistentClient.get_or_create_collection (chroma_store.py:41-59). */
+YRB_API int yrb_index_create(yrb_index** out, int device, int dim, int metric, int storage_dtype,
+                     int64_t reserve_rows);
+YRB_API int yrb_index_destroy(yrb_index* ix);
+YRB_API int yrb_index_reserve(yrb_index* ix, int64_t rows);
+/* rows = appended so far (incl. tombstoned); live = rows not tombstoned (collection.count(),
+ * chroma_store.py:249-255). */
+YRB_API int yrb_index_count(const yrb_index* ix, int64_t* out_rows, int64_t* out_live);
+YRB_API int yrb_index_info(const yrb_index* ix, int* out_dim, int* out_ld, int* out_metric,
+                   int* out_dtype, int* out_device, int64_t* out_capacity);
+
+/* collection.add(embeddings=…) (chroma_store.py:86): append n fp32 rows [n, dim]; cosine rows are
+ * L2-normalised (fp64 norm) and all rows rounded to the storage dtype on the device (kernel K5).
+ * New rows get ids [rows, rows+n). */
+YRB_API int yrb_index_append_host_f32(yrb_index* ix, const float* rows, int64_t n);
+YRB_API int yrb_index_append_device_f32(yrb_index* ix, const float* dev_rows, int64_t n, void* stream);
+/* stored rows decoded back to fp32 (Chunk.embedding of get_by_id, chroma_store.py:236-245). */
+YRB_API int yrb_index_read_rows(yrb_index* ix, const int64_t* row_ids, int64_t n, float* out_rows);
+/* collection.delete (chroma_store.py:150-160): tombstone / revive rows; tombstoned rows are
+ * invisible to search. */
+YRB_API int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int live);
+/* client.delete_collection + recreate (chroma_store.py:257-272). */
+YRB_API int yrb_index_clear(yrb_index* ix);
+
+/* ------------------------------------------------------------------ metadata filter
+ * Columnar metadata resident on the device, written by the host as chunks are added.  A column
+ * holds ONE (field, type) pair; `present` marks rows that have the field with that type. */
+#define YRB_COL_I64 0   /* int metadata (chunk_index, *_min_stamp, …) */
+#define YRB_COL_F64 1   /* float metadata (importance_score, …) */
+#define YRB_COL_CODE 2  /* dictionary-coded str, int32 codes assigned by the host */
+#define YRB_COL_BOOL 3  /* uint8 0/1 */
+YRB_API int yrb_index_column_write(yrb_index* ix, int col, int col_type, int64_t row_begin, int64_t n,
+                           const void* values, const uint8_t* present /* n bytes 0/1 */);
+
+#define YRB_OP_EQ 0
+#define YRB_OP_NE 1
+#define YRB_OP_GT 2
+#define YRB_OP_GTE 3
+#define YRB_OP_LT 4
+#define YRB_OP_LTE 5
+#define YRB_OP_IN 6
+#define YRB_OP_NIN 7
+/* a leaf with col < 0 refers to a (field,type) no row has: EQ/IN/GT… → false, NE/NIN → true */
+typedef struct yrb_where_leaf {
+    int32_t col;            /* column id given to yrb_index_column_write, or -1 */
+    int32_t op;             /* YRB_OP_* */
+    int32_t operand_begin;  /* first operand in yrb_where.operands */
+    int32_t operand_count;  /* 1, or the list length for IN / NIN */
+} yrb_where_leaf;
+#define YRB_TOK_AND (-1)
+#define YRB_TOK_OR (-2)
+#define YRB_TOK_NOT (-3)
+#define YRB_WHERE_MAX_LEAVES 64
+#define YRB_WHERE_MAX_OPERANDS 256
+#define YRB_WHERE_MAX_TOKENS 160
+/* a compiled Chroma `where` tree (chroma_store.py:104-120): postfix over leaves. */
+typedef struct yrb_where {
+    const yrb_where_leaf* leaves;
+    int32_t n_leaves;
+    const int64_t* operands; /* raw 8-byte patterns: int64, double, or int32 code / bool widened */
+    int32_t n_operands;
+    const int32_t* postfix;  /* token ≥ 0 = push leaf; YRB_TOK_* = operator */
+    int32_t n_postfix;
+} yrb_where;
+/* evaluate `w` over all rows (kernel K4) AND the live bits.  out_mask (host, may be NULL) gets
+ * ceil(rows/32) uint32 words, bit i of word j = row 32j+i; out_pass = number of passing rows. */
+YRB_API int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64_t* out_pass);
+
+/* ------------------------------------------------------------------ search
+ * stands in for collection.query(query_embeddings, n_results=k, where=…) (chroma_store.py:118-120),
+ * exact instead of HNSW.  queries: fp32 [nq, dim] (normalised + rounded on the device for cosine).
+ * Filter: `w` (compiled where, evaluated on the device) and/or `mask` (host bitmask, ceil(rows/32)
+ * words, shared by all queries); both NULL = all live rows.  Pre-filter semantics.
+ * Outputs per query q: out_ids[q*k + j] (row id, -1 padding), out_scores[q*k + j], ordered
+ * (score desc, id asc); out_counts[q] = number of valid results (≤ k). */
+YRB_API int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w,
+                     const uint32_t* mask, int64_t* out_ids, float* out_scores,
+                     int32_t* out_counts);
+
+/* All-device variant for resident inputs (bench `value`, sharded search): queries fp32 [nq, dim]
+ * on the device, mask device words or NULL, outputs = nq*k packed 64-bit selection keys
+ * (see yrb_key_*), best first, 0 = empty slot.  Asynchronous on `stream`. */
+YRB_API int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k,
+                            const uint32_t* dev_mask, uint64_t* dev_out_keys, void* stream);
+
+/* The top-k merge collective's local step (kernel K3): `parts` sorted lists of k keys
+ * per query, laid out [parts][nq][k] (the NCCL all-gather buffer, part p = rank p's shard) →
+ * out_ids (global id = row_base[p] + local row), out_scores, out_counts.  All device pointers. */
+YRB_API int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int nq, int k,
+                          const int64_t* dev_row_base, int64_t* dev_out_ids, float* dev_out_scores,
+                          int32_t* dev_out_counts, void* stream);
+
+/* Force a kernel family for tests/bench: 0 auto, 1 K1 (GEMV + in-register top-k),
+ * 2 K2 (tcgen05 GEMM + fused top-k epilogue), 3 K6 (score matrix + radix select). */
+YRB_API int yrb_index_set_path(yrb_index* ix, int path);
+/* launches issued by this index since creation (bench `gpu_launches`), and the duration in ms of
+ * the dominant kernel of the last search measured with CUDA events when enabled. */
+YRB_API int yrb_index_stats(const yrb_index* ix, int64_t* out_kernel_launches);
+
+/* selection key = (monotone(score) << 32) | ~row : larger key = better (score desc, row asc) */
+static inline uint32_t yrb_key_row(uint64_t key) { return ~(uint32_t)(key & 0xffffffffu); }
+static inline float yrb_key_score(uint64_t key) {
+    uint32_t m = (uint32_t)(key >> 32);
+    uint32_t u = (m & 0x80000000u) ? (m & 0x7fffffffu) : ~m;
+    union { uint32_t u; float f; } c;
+    c.u = u;
+    return c.f;
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YRB200_H */

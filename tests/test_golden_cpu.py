@@ -1,0 +1,71 @@
+"""Pins the oracle and the host-side mirrors to outputs of the reference's own (unmodified) Python
+glue, captured by tests/golden/make_golden.py.  CPU only."""
+
+import asyncio
+
+import numpy as np
+import pytest
+
+from oracle import exact_search as ox
+from tests.golden_util import GOLDEN, compare_with_golden, golden_chunks
+from tests.oracle_store import OracleStore
+from youtu_rag_b200 import RetrieverConfig, VectorRetriever
+from youtu_rag_b200.base import BaseEmbedder
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+def test_oracle_reproduces_reference_chroma_glue(metric):
+    store = OracleStore(metric, "f32")
+    asyncio.run(store.add_chunks(golden_chunks()))
+    n = 0
+    for rec in GOLDEN["chroma"]:
+        if rec["metric"] != metric:
+            continue
+        q = GOLDEN["queries"][rec["query"]]
+        if "error" in rec:
+            with pytest.raises(ValueError):
+                asyncio.run(store.search(q, rec["top_k"], rec["filters"]))
+        else:
+            got = asyncio.run(store.search(q, rec["top_k"], rec["filters"]))
+            compare_with_golden(got, rec["results"], tol=2e-6)
+        n += 1
+    assert n == 136
+
+
+def test_faiss_restatement_reproduces_reference_faiss_glue():
+    x = np.asarray(GOLDEN["corpus"]["embeddings"], np.float32)
+    metas = GOLDEN["corpus"]["metadatas"]
+    ids = [f"doc{i // 8}_chunk_{i % 8}" for i in range(len(metas))]
+    for rec in GOLDEN["faiss"]:
+        rows = ox.l2_normalize(x) if rec["metric"] == "cosine" else x
+        keep = None
+        if rec["filters"]:
+            keep = lambda i, f=rec["filters"]: all(metas[i].get(k) == v for k, v in f.items())
+        got_ids, got_s = ox.faiss_flat_search(rows, np.asarray(GOLDEN["queries"][rec["query"]], np.float32), rec["top_k"],
+                                              rec["metric"], keep)
+        want = rec["results"]
+        assert len(want) == got_ids.shape[0]
+        np.testing.assert_allclose(got_s, [w["score"] for w in want], rtol=2e-5, atol=2e-6)
+        for g, w, s in zip(got_ids.tolist(), want, got_s.tolist()):
+            # fp32 BLAS may order exact duplicates (rows 3/5) either way, also across the k-th boundary
+            assert ids[g] == w["id"] or abs(s - w["score"]) < 1e-6
+
+
+class _Emb(BaseEmbedder):
+    async def embed_texts(self, texts):
+        return [GOLDEN["queries"][int(t)] for t in texts]
+
+    async def embed_query(self, query):
+        return GOLDEN["queries"][int(query)]
+
+
+def test_retriever_mirror_reproduces_reference_retriever():
+    store = OracleStore("cosine", "f32")
+    asyncio.run(store.add_chunks(golden_chunks()))
+    for rec in GOLDEN["retriever"]:
+        r = VectorRetriever(store, _Emb(), RetrieverConfig(top_k=4, similarity_threshold=rec["config_threshold"]))
+        single = asyncio.run(r.retrieve("1", **rec["kwargs"]))
+        batch = asyncio.run(r.batch_retrieve(["0", "1", "2"], top_k=3, **rec["kwargs"]))
+        for got, want in [(single, rec["single"])] + list(zip(batch, rec["batch"])):
+            assert [x.rank for x in got] == [w["rank"] for w in want]
+            compare_with_golden([(x.chunk, x.score) for x in got], want, tol=2e-6)

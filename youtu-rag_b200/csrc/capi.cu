@@ -1,0 +1,784 @@
+// capi.cu — the C ABI declared in include/yrb200.h: one `yrb_index` = one collection's rows,
+// tombstones and metadata columns resident on one B200, plus the search entry points that chain
+// the kernels (K5 query prep → K4 filter → K1/K2/K6 scan+select → K3 merge → decode).
+// The reference interface each entry stands in for is cited in the header.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/yrb200.h"
+#include "k2_batched.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorMemoryAllocation ? YRB_ERR_NOMEM : YRB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
+    } while (0)
+
+struct Column {
+    int type = -1;
+    void* values = nullptr;       // device, capacity rows
+    uint32_t* present = nullptr;  // device bitmask, capacity words
+    std::vector<uint32_t> present_host;
+};
+
+int col_width(int t) { return t == YRB_COL_I64 || t == YRB_COL_F64 ? 8 : (t == YRB_COL_CODE ? 4 : 1); }
+
+int64_t mask_words(int64_t rows) { return (((rows + 31) / 32) + 1) & ~int64_t(1); }
+
+}  // namespace
+
+struct yrb_index {
+    int device = 0, dim = 0, ld = 0, metric = 0, dtype = 0, sm_count = 148;
+    int64_t rows = 0, capacity = 0, n_dead = 0;
+    void* d_rows = nullptr;
+    float* d_sqnorm = nullptr;
+    uint32_t* d_live = nullptr;  // mask_words(capacity)
+    uint32_t* d_mask = nullptr;  // filter scratch, same size
+    std::vector<uint32_t> h_live;
+    std::map<int, Column> cols;
+    cudaStream_t stream = nullptr;
+    // search scratch
+    int nq_cap = 0, k_cap = 0;
+    float* d_qf32 = nullptr;
+    void* d_q = nullptr;
+    float* d_qsq = nullptr;
+    uint64_t* d_parts = nullptr;
+    uint64_t* d_keys = nullptr;
+    uint64_t* d_mscratch = nullptr;
+    int64_t* d_ids = nullptr;
+    float* d_scores = nullptr;
+    int32_t* d_counts = nullptr;
+    float* d_rowscores = nullptr;  // K6, capacity floats
+    void* d_select = nullptr;
+    size_t select_bytes = 0;
+    yrb::WhereProgDev* d_prog = nullptr;
+    yrb::WhereProgDev* h_prog = nullptr;  // pinned
+    unsigned long long* d_pass = nullptr;
+    // pinned staging
+    float* h_q = nullptr;
+    int64_t* h_ids = nullptr;
+    float* h_scores = nullptr;
+    int32_t* h_counts = nullptr;
+    void* h_stage = nullptr;
+    size_t stage_bytes = 0;
+    yrb::K2State* k2 = nullptr;
+    int path = 0;
+    int64_t launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+int set_dev(const yrb_index* ix) {
+    CK(cudaSetDevice(ix->device));
+    return YRB_OK;
+}
+
+template <typename T>
+int regrow(T** p, size_t old_bytes, size_t new_bytes, bool zero_tail, cudaStream_t st) {
+    T* np_ = nullptr;
+    CK(cudaMalloc(reinterpret_cast<void**>(&np_), new_bytes ? new_bytes : 1));
+    if (*p && old_bytes) CK(cudaMemcpyAsync(np_, *p, std::min(old_bytes, new_bytes), cudaMemcpyDeviceToDevice, st));
+    if (zero_tail && new_bytes > old_bytes)
+        CK(cudaMemsetAsync(reinterpret_cast<char*>(np_) + old_bytes, 0, new_bytes - old_bytes, st));
+    CK(cudaStreamSynchronize(st));
+    if (*p) CK(cudaFree(*p));
+    *p = np_;
+    return YRB_OK;
+}
+
+int ensure_capacity(yrb_index* ix, int64_t want) {
+    if (want <= ix->capacity) return YRB_OK;
+    int64_t cap = std::max<int64_t>(want, ix->capacity + ix->capacity / 2);
+    cap = std::max<int64_t>(cap, 1024);
+    cap = (cap + 255) / 256 * 256;
+    const size_t es = yrb::elem_size(ix->dtype);
+    int rc;
+    if ((rc = regrow(reinterpret_cast<char**>(&ix->d_rows), (size_t)ix->rows * ix->ld * es, (size_t)cap * ix->ld * es,
+                     false, ix->stream)))
+        return rc;
+    if ((rc = regrow(&ix->d_sqnorm, (size_t)ix->rows * 4, (size_t)cap * 4, false, ix->stream))) return rc;
+    const size_t ow = (size_t)mask_words(ix->capacity) * 4, nw = (size_t)mask_words(cap) * 4;
+    if ((rc = regrow(&ix->d_live, ix->capacity ? ow : 0, nw, true, ix->stream))) return rc;
+    if ((rc = regrow(&ix->d_mask, 0, nw, true, ix->stream))) return rc;
+    if ((rc = regrow(&ix->d_rowscores, 0, (size_t)cap * 4, false, ix->stream))) return rc;
+    ix->h_live.resize(mask_words(cap), 0u);
+    for (auto& kv : ix->cols) {
+        Column& c = kv.second;
+        const size_t w = col_width(c.type);
+        if ((rc = regrow(reinterpret_cast<char**>(&c.values), (size_t)ix->capacity * w, (size_t)cap * w, true,
+                         ix->stream)))
+            return rc;
+        if ((rc = regrow(&c.present, ix->capacity ? ow : 0, nw, true, ix->stream))) return rc;
+        c.present_host.resize(mask_words(cap), 0u);
+    }
+    ix->capacity = cap;
+    if (ix->k2) yrb::k2_invalidate(ix->k2);
+    return YRB_OK;
+}
+
+int ensure_stage(yrb_index* ix, size_t bytes) {
+    if (bytes <= ix->stage_bytes) return YRB_OK;
+    if (ix->h_stage) CK(cudaFreeHost(ix->h_stage));
+    ix->h_stage = nullptr;
+    ix->stage_bytes = 0;
+    CK(cudaMallocHost(&ix->h_stage, bytes));
+    ix->stage_bytes = bytes;
+    return YRB_OK;
+}
+
+#define FREE_DEV(p)            \
+    do {                       \
+        if (p) cudaFree(p);    \
+        p = nullptr;           \
+    } while (0)
+#define FREE_HOST(p)            \
+    do {                        \
+        if (p) cudaFreeHost(p); \
+        p = nullptr;            \
+    } while (0)
+
+void free_scratch(yrb_index* ix) {
+    FREE_DEV(ix->d_qf32);
+    FREE_DEV(ix->d_q);
+    FREE_DEV(ix->d_qsq);
+    FREE_DEV(ix->d_parts);
+    FREE_DEV(ix->d_keys);
+    FREE_DEV(ix->d_mscratch);
+    FREE_DEV(ix->d_ids);
+    FREE_DEV(ix->d_scores);
+    FREE_DEV(ix->d_counts);
+    FREE_HOST(ix->h_q);
+    FREE_HOST(ix->h_ids);
+    FREE_HOST(ix->h_scores);
+    FREE_HOST(ix->h_counts);
+    ix->nq_cap = ix->k_cap = 0;
+}
+
+int ensure_scratch(yrb_index* ix, int nq, int k) {
+    if (nq <= ix->nq_cap && k <= ix->k_cap) return YRB_OK;
+    const int nqc = std::max(nq, ix->nq_cap), kc = std::max(k, ix->k_cap);
+    CK(cudaStreamSynchronize(ix->stream));
+    free_scratch(ix);
+    const int parts = std::max(yrb::k1_parts(ix->sm_count), yrb::k2_parts(ix->sm_count));
+    const size_t es = yrb::elem_size(ix->dtype);
+    CK(cudaMalloc(&ix->d_qf32, (size_t)nqc * ix->dim * 4));
+    CK(cudaMalloc(&ix->d_q, (size_t)nqc * ix->ld * es));
+    CK(cudaMalloc(&ix->d_qsq, (size_t)nqc * 4));
+    CK(cudaMalloc(&ix->d_parts, (size_t)parts * nqc * kc * 8));
+    CK(cudaMalloc(&ix->d_keys, (size_t)nqc * kc * 8));
+    CK(cudaMalloc(&ix->d_mscratch, (size_t)parts * nqc * kc * 8));
+    CK(cudaMalloc(&ix->d_ids, (size_t)nqc * kc * 8));
+    CK(cudaMalloc(&ix->d_scores, (size_t)nqc * kc * 4));
+    CK(cudaMalloc(&ix->d_counts, (size_t)nqc * 4));
+    CK(cudaMallocHost(&ix->h_q, (size_t)nqc * ix->dim * 4));
+    CK(cudaMallocHost(&ix->h_ids, (size_t)nqc * kc * 8));
+    CK(cudaMallocHost(&ix->h_scores, (size_t)nqc * kc * 4));
+    CK(cudaMallocHost(&ix->h_counts, (size_t)nqc * 4));
+    ix->nq_cap = nqc;
+    ix->k_cap = kc;
+    return YRB_OK;
+}
+
+// upload the host mirror of a bitmask range [w0, w1)
+int upload_words(uint32_t* dev, const std::vector<uint32_t>& host, int64_t w0, int64_t w1, cudaStream_t st) {
+    if (w1 <= w0) return YRB_OK;
+    CK(cudaMemcpyAsync(dev + w0, host.data() + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return YRB_OK;
+}
+
+int mark_appended(yrb_index* ix, int64_t r0, int64_t n) {
+    for (int64_t r = r0; r < r0 + n; ++r) ix->h_live[r >> 5] |= (1u << (r & 31));
+    return upload_words(ix->d_live, ix->h_live, r0 >> 5, ((r0 + n - 1) >> 5) + 1, ix->stream);
+}
+
+int build_prog(yrb_index* ix, const yrb_where* w) {
+    if (!w) return fail(YRB_ERR_INVALID, "where is NULL");
+    if (w->n_leaves < 0 || w->n_leaves > YRB_WHERE_MAX_LEAVES) return fail(YRB_ERR_INVALID, "where: too many leaves (%d > %d)", w->n_leaves, YRB_WHERE_MAX_LEAVES);
+    if (w->n_operands < 0 || w->n_operands > YRB_WHERE_MAX_OPERANDS) return fail(YRB_ERR_INVALID, "where: too many operands (%d > %d)", w->n_operands, YRB_WHERE_MAX_OPERANDS);
+    if (w->n_postfix < 0 || w->n_postfix > YRB_WHERE_MAX_TOKENS) return fail(YRB_ERR_INVALID, "where: too many tokens (%d > %d)", w->n_postfix, YRB_WHERE_MAX_TOKENS);
+    yrb::WhereProgDev* p = ix->h_prog;
+    memset(p, 0, sizeof *p);
+    p->n_leaves = w->n_leaves;
+    p->n_postfix = w->n_postfix;
+    for (int i = 0; i < w->n_leaves; ++i) {
+        const yrb_where_leaf& l = w->leaves[i];
+        if (l.op < YRB_OP_EQ || l.op > YRB_OP_NIN) return fail(YRB_ERR_INVALID, "where leaf %d: bad op %d", i, l.op);
+        if (l.operand_count < 1 || l.operand_begin < 0 || l.operand_begin + l.operand_count > w->n_operands)
+            return fail(YRB_ERR_INVALID, "where leaf %d: operand range out of bounds", i);
+        yrb::WhereLeafDev& d = p->leaves[i];
+        d.op = l.op;
+        d.operand_begin = l.operand_begin;
+        d.operand_count = l.operand_count;
+        d.col_type = -1;
+        if (l.col >= 0) {
+            auto it = ix->cols.find(l.col);
+            if (it == ix->cols.end()) return fail(YRB_ERR_INVALID, "where leaf %d: unknown column %d", i, l.col);
+            d.col_type = it->second.type;
+            d.values = it->second.values;
+            d.present = it->second.present;
+        }
+    }
+    for (int i = 0; i < w->n_operands; ++i) p->operands[i] = w->operands[i];
+    int depth = 0;
+    for (int i = 0; i < w->n_postfix; ++i) {
+        const int t = w->postfix[i];
+        if (t >= 0) {
+            if (t >= w->n_leaves) return fail(YRB_ERR_INVALID, "where token %d: leaf %d out of range", i, t);
+            ++depth;
+        } else if (t == YRB_TOK_NOT) {
+            if (depth < 1) return fail(YRB_ERR_INVALID, "where: malformed postfix");
+        } else if (t == YRB_TOK_AND || t == YRB_TOK_OR) {
+            if (depth < 2) return fail(YRB_ERR_INVALID, "where: malformed postfix");
+            --depth;
+        } else {
+            return fail(YRB_ERR_INVALID, "where token %d: bad token %d", i, t);
+        }
+        if (depth > 64) return fail(YRB_ERR_INVALID, "where: expression too deep");
+        p->postfix[i] = t;
+    }
+    if (w->n_postfix > 0 && depth != 1) return fail(YRB_ERR_INVALID, "where: malformed postfix");
+    return YRB_OK;
+}
+
+// evaluates w (and/or ANDs a device mask) into ix->d_mask; returns the mask pointer to scan with
+int resolve_mask(yrb_index* ix, const yrb_where* w, const uint32_t* dev_extra, const uint32_t** out, cudaStream_t st,
+                 bool count) {
+    const uint32_t* live = ix->n_dead > 0 ? ix->d_live : nullptr;
+    if (w) {
+        int rc = build_prog(ix, w);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ix->d_prog, ix->h_prog, sizeof(yrb::WhereProgDev), cudaMemcpyHostToDevice, st));
+        if (count) CK(cudaMemsetAsync(ix->d_pass, 0, 8, st));
+        CK(yrb::launch_where(ix->d_prog, ix->rows, live, dev_extra, ix->d_mask, count ? ix->d_pass : nullptr, st));
+        ix->launches++;
+        *out = ix->d_mask;
+    } else if (dev_extra) {
+        if (live) {
+            CK(yrb::launch_mask_and(dev_extra, live, mask_words(ix->rows), ix->d_mask, st));
+            ix->launches++;
+            *out = ix->d_mask;
+        } else {
+            *out = dev_extra;
+        }
+    } else {
+        *out = live;
+    }
+    return YRB_OK;
+}
+
+// queries already prepared in ix->d_q / ix->d_qsq; writes nq*k keys
+int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* out_keys, cudaStream_t st) {
+    int path = ix->path;
+    if (path == 0) {
+        if (k > YRB_FUSED_K_MAX) path = 3;
+        else if (nq >= 8 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
+        else path = 1;
+    }
+    if (path == 2 && !yrb::k2_supported(ix->dtype, ix->dim, k))
+        return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage and k <= %d", YRB_FUSED_K_MAX);
+    if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
+        return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
+    const size_t es = yrb::elem_size(ix->dtype);
+    if (path == 2) {
+        int launches = 0;
+        int rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
+                                ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ix->d_mscratch, ix->sm_count, st,
+                                &launches, g_err);
+        ix->launches += launches;
+        return rc;
+    }
+    if (path == 1) {
+        const int parts = yrb::k1_parts(ix->sm_count);
+        for (int j = 0; j < nq; ++j) {
+            uint64_t* pk = ix->d_parts + (size_t)j * parts * k;
+            CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld,
+                              reinterpret_cast<const char*>(ix->d_q) + (size_t)j * ix->ld * es, ix->d_qsq + j,
+                              ix->d_sqnorm, ix->metric, mask, k, pk, ix->sm_count, st));
+            CK(yrb::launch_merge_keys(pk, parts, 1, k, out_keys + (size_t)j * k, ix->d_mscratch, st));
+            ix->launches += 2;
+        }
+        return YRB_OK;
+    }
+    // path 3: score vector + radix select, any k
+    const size_t need = yrb::select_scratch_bytes(ix->rows, k);
+    if (need > ix->select_bytes) {
+        CK(cudaStreamSynchronize(st));
+        FREE_DEV(ix->d_select);
+        CK(cudaMalloc(&ix->d_select, need));
+        ix->select_bytes = need;
+    }
+    for (int j = 0; j < nq; ++j) {
+        CK(yrb::launch_scores(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld,
+                              reinterpret_cast<const char*>(ix->d_q) + (size_t)j * ix->ld * es, ix->d_qsq + j,
+                              ix->d_sqnorm, ix->metric, mask, ix->d_rowscores, ix->sm_count, st));
+        CK(yrb::launch_select(ix->d_rowscores, ix->rows, k, out_keys + (size_t)j * k, ix->d_select, ix->sm_count, st));
+        ix->launches += 2;
+    }
+    return YRB_OK;
+}
+
+int append_device_locked(yrb_index* ix, const float* dev_rows, int64_t n, cudaStream_t st) {
+    int rc = ensure_capacity(ix, ix->rows + n);
+    if (rc) return rc;
+    const size_t es = yrb::elem_size(ix->dtype);
+    CK(yrb::launch_ingest(dev_rows, n, ix->dim, ix->ld, ix->metric, ix->dtype,
+                          reinterpret_cast<char*>(ix->d_rows) + (size_t)ix->rows * ix->ld * es,
+                          ix->d_sqnorm + ix->rows, st));
+    ix->launches++;
+    CK(cudaStreamSynchronize(st));
+    rc = mark_appended(ix, ix->rows, n);
+    if (rc) return rc;
+    ix->rows += n;
+    return YRB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yrb_abi_version(void) { return YRB_ABI_VERSION; }
+const char* yrb_last_error(void) { return g_err.c_str(); }
+
+int yrb_device_count(int* out_count) {
+    if (!out_count) return fail(YRB_ERR_INVALID, "out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        *out_count = 0;
+        cudaGetLastError();
+        return fail(YRB_ERR_NODEVICE, "no CUDA device visible (%s); this backend has no CPU fallback",
+                    e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    *out_count = ok;
+    if (!ok) return fail(YRB_ERR_NODEVICE, "no sm_100 (B200) device among %d CUDA devices; no fallback path", n);
+    return YRB_OK;
+}
+
+int yrb_index_create(yrb_index** out, int device, int dim, int metric, int storage_dtype, int64_t reserve_rows) {
+    if (!out) return fail(YRB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (dim < 1 || dim > 65536) return fail(YRB_ERR_INVALID, "dim %d out of range [1, 65536]", dim);
+    if (metric < 0 || metric > 2) return fail(YRB_ERR_INVALID, "unknown metric %d", metric);
+    if (storage_dtype < 0 || storage_dtype > 1) return fail(YRB_ERR_INVALID, "unknown storage dtype %d", storage_dtype);
+    int n = 0;
+    int rc = yrb_device_count(&n);
+    if (rc) return rc;
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(YRB_ERR_NODEVICE, "device %d is not sm_100 (compute capability %d.x)", device, major);
+    yrb_index* ix = new (std::nothrow) yrb_index();
+    if (!ix) return fail(YRB_ERR_NOMEM, "host allocation failed");
+    ix->device = device;
+    ix->dim = dim;
+    ix->metric = metric;
+    ix->dtype = storage_dtype;
+    ix->ld = yrb::row_ld(dim, storage_dtype);
+    auto bail = [&](int code) {
+        yrb_index_destroy(ix);
+        return code;
+    };
+#define CKB(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return bail(fail(YRB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__)); \
+    } while (0)
+    CKB(cudaSetDevice(device));
+    CKB(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CKB(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CKB(cudaMalloc(&ix->d_prog, sizeof(yrb::WhereProgDev)));
+    CKB(cudaMallocHost(&ix->h_prog, sizeof(yrb::WhereProgDev)));
+    CKB(cudaMalloc(&ix->d_pass, 8));
+#undef CKB
+    ix->k2 = yrb::k2_create();
+    rc = ensure_capacity(ix, std::max<int64_t>(reserve_rows, 1));
+    if (rc) return bail(rc);
+    *out = ix;
+    return YRB_OK;
+}
+
+int yrb_index_destroy(yrb_index* ix) {
+    if (!ix) return YRB_OK;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    free_scratch(ix);
+    FREE_DEV(ix->d_rows);
+    FREE_DEV(ix->d_sqnorm);
+    FREE_DEV(ix->d_live);
+    FREE_DEV(ix->d_mask);
+    FREE_DEV(ix->d_rowscores);
+    FREE_DEV(ix->d_select);
+    FREE_DEV(ix->d_prog);
+    FREE_DEV(ix->d_pass);
+    FREE_HOST(ix->h_prog);
+    FREE_HOST(ix->h_stage);
+    for (auto& kv : ix->cols) {
+        FREE_DEV(kv.second.values);
+        FREE_DEV(kv.second.present);
+    }
+    if (ix->k2) yrb::k2_destroy(ix->k2);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return YRB_OK;
+}
+
+int yrb_index_reserve(yrb_index* ix, int64_t rows) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    return ensure_capacity(ix, rows);
+}
+
+int yrb_index_count(const yrb_index* ix, int64_t* out_rows, int64_t* out_live) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (out_rows) *out_rows = ix->rows;
+    if (out_live) *out_live = ix->rows - ix->n_dead;
+    return YRB_OK;
+}
+
+int yrb_index_info(const yrb_index* ix, int* out_dim, int* out_ld, int* out_metric, int* out_dtype, int* out_device,
+                   int64_t* out_capacity) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (out_dim) *out_dim = ix->dim;
+    if (out_ld) *out_ld = ix->ld;
+    if (out_metric) *out_metric = ix->metric;
+    if (out_dtype) *out_dtype = ix->dtype;
+    if (out_device) *out_device = ix->device;
+    if (out_capacity) *out_capacity = ix->capacity;
+    return YRB_OK;
+}
+
+int yrb_index_append_host_f32(yrb_index* ix, const float* rows, int64_t n) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || (n > 0 && !rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
+    if (n == 0) return YRB_OK;
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if (ix->rows + n > 0xfffffffell) return fail(YRB_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
+    if ((rc = ensure_capacity(ix, ix->rows + n))) return rc;
+    // staged in chunks: pageable → pinned → device fp32 scratch → K5 into place
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(32u << 20) / ((int64_t)ix->dim * 4));
+    if ((rc = ensure_stage(ix, (size_t)chunk * ix->dim * 4))) return rc;
+    float* d_tmp = nullptr;
+    CK(cudaMalloc(&d_tmp, (size_t)chunk * ix->dim * 4));
+    for (int64_t r = 0; r < n; r += chunk) {
+        const int64_t m = std::min(chunk, n - r);
+        memcpy(ix->h_stage, rows + r * ix->dim, (size_t)m * ix->dim * 4);
+        cudaError_t e = cudaMemcpyAsync(d_tmp, ix->h_stage, (size_t)m * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream);
+        if (e == cudaSuccess) {
+            rc = append_device_locked(ix, d_tmp, m, ix->stream);
+        } else {
+            rc = fail(YRB_ERR_CUDA, "H2D copy of rows failed: %s", cudaGetErrorString(e));
+        }
+        if (rc) {
+            cudaFree(d_tmp);
+            return rc;
+        }
+    }
+    CK(cudaFree(d_tmp));
+    return YRB_OK;
+}
+
+int yrb_index_append_device_f32(yrb_index* ix, const float* dev_rows, int64_t n, void* stream) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || (n > 0 && !dev_rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
+    if (n == 0) return YRB_OK;
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if (ix->rows + n > 0xfffffffell) return fail(YRB_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (stream) CK(cudaStreamSynchronize(st));  // producer of dev_rows may still be running on `stream`
+    return append_device_locked(ix, dev_rows, n, st);
+}
+
+int yrb_index_read_rows(yrb_index* ix, const int64_t* row_ids, int64_t n, float* out_rows) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || (n > 0 && (!row_ids || !out_rows))) return fail(YRB_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    const size_t es = yrb::elem_size(ix->dtype);
+    std::vector<unsigned char> tmp((size_t)ix->ld * es);
+    // coalesce runs of consecutive ids into one copy
+    int64_t i = 0;
+    while (i < n) {
+        int64_t j = i;
+        while (j + 1 < n && row_ids[j + 1] == row_ids[j] + 1) ++j;
+        const int64_t r0 = row_ids[i], cnt = j - i + 1;
+        if (r0 < 0 || r0 + cnt > ix->rows) return fail(YRB_ERR_INVALID, "row id %lld out of range", (long long)r0);
+        tmp.resize((size_t)cnt * ix->ld * es);
+        CK(cudaMemcpyAsync(tmp.data(), reinterpret_cast<char*>(ix->d_rows) + (size_t)r0 * ix->ld * es, tmp.size(),
+                           cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        for (int64_t r = 0; r < cnt; ++r) {
+            float* o = out_rows + (i + r) * ix->dim;
+            if (ix->dtype == YRB_DTYPE_F32) {
+                memcpy(o, tmp.data() + (size_t)r * ix->ld * 4, (size_t)ix->dim * 4);
+            } else {
+                const uint16_t* b = reinterpret_cast<const uint16_t*>(tmp.data()) + (size_t)r * ix->ld;
+                for (int d = 0; d < ix->dim; ++d) {
+                    uint32_t u = (uint32_t)b[d] << 16;
+                    memcpy(&o[d], &u, 4);
+                }
+            }
+        }
+        i = j + 1;
+    }
+    return YRB_OK;
+}
+
+int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int live) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || (n > 0 && !row_ids)) return fail(YRB_ERR_INVALID, "bad arguments");
+    if (n == 0) return YRB_OK;
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i)
+        if (row_ids[i] < 0 || row_ids[i] >= ix->rows)
+            return fail(YRB_ERR_INVALID, "row id %lld out of range", (long long)row_ids[i]);
+    int64_t wmin = INT64_MAX, wmax = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t r = row_ids[i], w = r >> 5;
+        const uint32_t bit = 1u << (r & 31);
+        const bool was = ix->h_live[w] & bit;
+        if (live && !was) {
+            ix->h_live[w] |= bit;
+            ix->n_dead--;
+        } else if (!live && was) {
+            ix->h_live[w] &= ~bit;
+            ix->n_dead++;
+        }
+        wmin = std::min(wmin, w);
+        wmax = std::max(wmax, w);
+    }
+    return upload_words(ix->d_live, ix->h_live, wmin, wmax + 1, ix->stream);
+}
+
+int yrb_index_clear(yrb_index* ix) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->rows = 0;
+    ix->n_dead = 0;
+    std::fill(ix->h_live.begin(), ix->h_live.end(), 0u);
+    CK(cudaMemsetAsync(ix->d_live, 0, (size_t)mask_words(ix->capacity) * 4, ix->stream));
+    for (auto& kv : ix->cols) {
+        FREE_DEV(kv.second.values);
+        FREE_DEV(kv.second.present);
+    }
+    ix->cols.clear();
+    CK(cudaStreamSynchronize(ix->stream));
+    return YRB_OK;
+}
+
+int yrb_index_column_write(yrb_index* ix, int col, int col_type, int64_t row_begin, int64_t n, const void* values,
+                           const uint8_t* present) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (col < 0) return fail(YRB_ERR_INVALID, "column id must be >= 0");
+    if (col_type < YRB_COL_I64 || col_type > YRB_COL_BOOL) return fail(YRB_ERR_INVALID, "bad column type %d", col_type);
+    if (n < 0 || row_begin < 0 || (n > 0 && (!values || !present))) return fail(YRB_ERR_INVALID, "bad arguments");
+    if (n == 0) return YRB_OK;
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if (row_begin + n > ix->rows) return fail(YRB_ERR_INVALID, "column rows [%lld,%lld) beyond appended rows %lld",
+                                               (long long)row_begin, (long long)(row_begin + n), (long long)ix->rows);
+    Column& c = ix->cols[col];
+    const size_t w = col_width(col_type);
+    if (c.type < 0) {
+        c.type = col_type;
+        if ((rc = regrow(reinterpret_cast<char**>(&c.values), 0, (size_t)ix->capacity * w, true, ix->stream))) return rc;
+        if ((rc = regrow(&c.present, 0, (size_t)mask_words(ix->capacity) * 4, true, ix->stream))) return rc;
+        c.present_host.assign(mask_words(ix->capacity), 0u);
+    } else if (c.type != col_type) {
+        return fail(YRB_ERR_INVALID, "column %d already has type %d", col, c.type);
+    }
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(c.values) + (size_t)row_begin * w, values, (size_t)n * w,
+                       cudaMemcpyHostToDevice, ix->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t r = row_begin + i;
+        if (present[i]) c.present_host[r >> 5] |= (1u << (r & 31));
+        else c.present_host[r >> 5] &= ~(1u << (r & 31));
+    }
+    return upload_words(c.present, c.present_host, row_begin >> 5, ((row_begin + n - 1) >> 5) + 1, ix->stream);
+}
+
+int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64_t* out_pass) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if (ix->rows == 0) {
+        if (out_pass) *out_pass = 0;
+        return YRB_OK;
+    }
+    yrb_where all = {nullptr, 0, nullptr, 0, nullptr, 0};
+    const uint32_t* m = nullptr;
+    if ((rc = resolve_mask(ix, w ? w : &all, nullptr, &m, ix->stream, true))) return rc;
+    unsigned long long pass = 0;
+    CK(cudaMemcpyAsync(&pass, ix->d_pass, 8, cudaMemcpyDeviceToHost, ix->stream));
+    if (out_mask)
+        CK(cudaMemcpyAsync(out_mask, m, (size_t)((ix->rows + 31) / 32) * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    if (out_pass) *out_pass = (int64_t)pass;
+    return YRB_OK;
+}
+
+int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w, const uint32_t* mask,
+                     int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (nq < 1 || !queries) return fail(YRB_ERR_INVALID, "need at least one query");
+    if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
+    if (!out_ids || !out_scores) return fail(YRB_ERR_INVALID, "output buffers are NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    const int64_t live_rows = ix->rows - ix->n_dead;
+    if (live_rows == 0) {
+        for (int64_t i = 0; i < (int64_t)nq * k; ++i) {
+            out_ids[i] = -1;
+            out_scores[i] = -INFINITY;
+        }
+        if (out_counts)
+            for (int q = 0; q < nq; ++q) out_counts[q] = 0;
+        return YRB_OK;
+    }
+    // never select more than exist: keeps the fused paths usable for small collections
+    const int ke = (int)std::min<int64_t>(k, ix->rows);
+    if ((rc = ensure_scratch(ix, nq, ke))) return rc;
+    cudaStream_t st = ix->stream;
+    memcpy(ix->h_q, queries, (size_t)nq * ix->dim * 4);
+    CK(cudaMemcpyAsync(ix->d_qf32, ix->h_q, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, st));
+    CK(yrb::launch_ingest(ix->d_qf32, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
+    ix->launches++;
+    const uint32_t* dev_extra = nullptr;
+    uint32_t* d_user = nullptr;
+    if (mask) {
+        const int64_t nw = (ix->rows + 31) / 32, nwp = mask_words(ix->rows);
+        CK(cudaMalloc(&d_user, (size_t)nwp * 4));
+        cudaError_t e = cudaMemsetAsync(d_user, 0, (size_t)nwp * 4, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_user, mask, (size_t)nw * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && (ix->rows & 31)) {
+            // clear bits past the last row of the last word
+            uint32_t last = mask[nw - 1] & ((1u << (ix->rows & 31)) - 1u);
+            e = cudaMemcpyAsync(d_user + nw - 1, &last, 4, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (e != cudaSuccess) {
+            cudaFree(d_user);
+            return fail(YRB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
+        }
+        dev_extra = d_user;
+    }
+    const uint32_t* m = nullptr;
+    rc = resolve_mask(ix, w, dev_extra, &m, st, false);
+    if (!rc) rc = scan_select(ix, nq, ke, m, ix->d_keys, st);
+    if (!rc) {
+        cudaError_t e = yrb::launch_decode(ix->d_keys, nq, ke, ix->d_ids, ix->d_scores, ix->d_counts, st);
+        ix->launches++;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->h_ids, ix->d_ids, (size_t)nq * ke * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->h_scores, ix->d_scores, (size_t)nq * ke * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->h_counts, ix->d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(YRB_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
+    } else {
+        cudaStreamSynchronize(st);
+    }
+    if (d_user) cudaFree(d_user);
+    if (rc) return rc;
+    for (int q = 0; q < nq; ++q) {
+        for (int j = 0; j < k; ++j) {
+            const bool ok = j < ke;
+            out_ids[(int64_t)q * k + j] = ok ? ix->h_ids[(int64_t)q * ke + j] : -1;
+            out_scores[(int64_t)q * k + j] = ok ? ix->h_scores[(int64_t)q * ke + j] : -INFINITY;
+        }
+        if (out_counts) out_counts[q] = ix->h_counts[q];
+    }
+    return YRB_OK;
+}
+
+int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k, const uint32_t* dev_mask,
+                            uint64_t* dev_out_keys, void* stream) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (nq < 1 || !dev_queries || !dev_out_keys) return fail(YRB_ERR_INVALID, "bad arguments");
+    if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (ix->rows == 0) {
+        CK(cudaMemsetAsync(dev_out_keys, 0, (size_t)nq * k * 8, st));
+        return YRB_OK;
+    }
+    if (k > ix->rows) return fail(YRB_ERR_INVALID, "k=%d exceeds rows=%lld (device variant does not clamp)", k, (long long)ix->rows);
+    if ((rc = ensure_scratch(ix, nq, k))) return rc;
+    CK(yrb::launch_ingest(dev_queries, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
+    ix->launches++;
+    const uint32_t* m = nullptr;
+    if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
+    return scan_select(ix, nq, k, m, dev_out_keys, st);
+}
+
+int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int nq, int k, const int64_t* dev_row_base,
+                          int64_t* dev_out_ids, float* dev_out_scores, int32_t* dev_out_counts, void* stream) {
+    if (!dev_keys || !dev_row_base || !dev_out_ids || !dev_out_scores) return fail(YRB_ERR_INVALID, "NULL buffer");
+    if (parts < 1 || nq < 1 || k < 1) return fail(YRB_ERR_INVALID, "bad parts/nq/k");
+    if ((int64_t)parts * k > 2048) return fail(YRB_ERR_UNSUPPORTED, "parts*k = %lld exceeds 2048", (long long)parts * k);
+    CK(cudaSetDevice(device));
+    CK(yrb::launch_merge_global(dev_keys, parts, nq, k, dev_row_base, dev_out_ids, dev_out_scores, dev_out_counts,
+                                (cudaStream_t)stream));
+    return YRB_OK;
+}
+
+int yrb_index_set_path(yrb_index* ix, int path) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (path < 0 || path > 3) return fail(YRB_ERR_INVALID, "path must be 0..3");
+    ix->path = path;
+    return YRB_OK;
+}
+
+int yrb_index_stats(const yrb_index* ix, int64_t* out_kernel_launches) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (out_kernel_launches) *out_kernel_launches = ix->launches;
+    return YRB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+// K1 — single-query scan: HBM-bound GEMV + in-register running top-k + bitmask, one pass.
+//
+// Stands in for the inner loop of collection.query(query_embeddings=[q], n_results=k, where=…)
+// (utu/rag/storage/implementations/chroma_store.py:118-120) / faiss IndexFlat.search
+// (faiss_store.py:154), computed exactly.
+//
+// Shape of the work: every stored row is read once with 128-bit coalesced
+// streaming loads (a warp covers 512 contiguous bytes per instruction, R rows × 4 chunks = 16
+// loads in flight per lane); the query lives in shared memory as fp32; a row's score is a
+// warp butterfly sum; each warp keeps a sorted top-k of 64-bit keys spread over its lanes and
+// only touches it when a score beats the current k-th key.  Rows failing the bitmask are never
+// loaded.  Per-CTA lists are merged with a block bitonic sort; K3 merges the CTAs.
+// Algorithmic bytes per search: sel·N·ld·esize + N/8 (mask) + ld·esize (query) + parts·k·8.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace yrb {
+
+constexpr int K1_THREADS = 512;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_R = 4;   // rows per batch
+constexpr int K1_CU = 4;  // chunks per unrolled step
+
+int k1_parts(int sm_count) { return sm_count; }
+
+template <bool F32>
+__device__ __forceinline__ float dot_chunk(uint4 v, float4 qa, float4 qb, float acc) {
+    if (F32) {
+        acc = fmaf(__uint_as_float(v.x), qa.x, acc);
+        acc = fmaf(__uint_as_float(v.y), qa.y, acc);
+        acc = fmaf(__uint_as_float(v.z), qa.z, acc);
+        acc = fmaf(__uint_as_float(v.w), qa.w, acc);
+    } else {
+        acc = fmaf(__uint_as_float(v.x << 16), qa.x, acc);
+        acc = fmaf(__uint_as_float(v.x & 0xffff0000u), qa.y, acc);
+        acc = fmaf(__uint_as_float(v.y << 16), qa.z, acc);
+        acc = fmaf(__uint_as_float(v.y & 0xffff0000u), qa.w, acc);
+        acc = fmaf(__uint_as_float(v.z << 16), qb.x, acc);
+        acc = fmaf(__uint_as_float(v.z & 0xffff0000u), qb.y, acc);
+        acc = fmaf(__uint_as_float(v.w << 16), qb.z, acc);
+        acc = fmaf(__uint_as_float(v.w & 0xffff0000u), qb.w, acc);
+    }
+    return acc;
+}
+
+// query (storage dtype, ld16 uint4) → shared fp32, laid out [chunk][half][lane] float4 so that a
+// warp's LDS.128 is conflict-free.
+template <bool F32>
+__device__ __forceinline__ void stage_query(const uint4* __restrict__ qv, int ld16, int nch, float4* sq) {
+    constexpr int H = F32 ? 1 : 2;
+    for (int i = threadIdx.x; i < nch * 32; i += blockDim.x) {
+        const int c = i >> 5, l = i & 31;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < ld16) v = qv[i];
+        if (F32) {
+            sq[(c * H) * 32 + l] =
+                make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+        } else {
+            sq[(c * H) * 32 + l] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
+                                               __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+            sq[(c * H + 1) * 32 + l] = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u),
+                                                   __uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u));
+        }
+    }
+}
+
+// dot products of K1_R rows (row pointers rp[], warp-uniform validity va[]) with the staged query;
+// every lane returns the full sums.
+template <bool F32>
+__device__ __forceinline__ void rows_dot(const uint4* const (&rp)[K1_R], const bool (&va)[K1_R], int ld16, int nch,
+                                         const float4* sq, int lane, float (&acc)[K1_R]) {
+    constexpr int H = F32 ? 1 : 2;
+#pragma unroll
+    for (int r = 0; r < K1_R; ++r) acc[r] = 0.f;
+    for (int c0 = 0; c0 < nch; c0 += K1_CU) {
+        uint4 v[K1_R][K1_CU];
+#pragma unroll
+        for (int cc = 0; cc < K1_CU; ++cc) {
+            const int off = (c0 + cc) * 32 + lane;
+            const bool in = off < ld16;
+#pragma unroll
+            for (int r = 0; r < K1_R; ++r) {
+                v[r][cc] = make_uint4(0, 0, 0, 0);
+                if (in && va[r]) v[r][cc] = ldg_stream(rp[r] + off);
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < K1_CU; ++cc) {
+            const int c = c0 + cc;
+            if (c < nch) {
+                const float4 qa = sq[(c * H) * 32 + lane];
+                const float4 qb = F32 ? qa : sq[(c * H + 1) * 32 + lane];
+#pragma unroll
+                for (int r = 0; r < K1_R; ++r) acc[r] = dot_chunk<F32>(v[r][cc], qa, qb, acc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < K1_R; ++r) acc[r] = warp_sum(acc[r]);
+}
+
+template <bool F32, int KPL, bool HAS_MASK>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+    k1_scan_topk(const uint4* __restrict__ rows, int64_t n_rows, int ld16, int nch, const uint4* __restrict__ qv,
+                 const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm, int l2,
+                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ part_keys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* sq = reinterpret_cast<float4*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+
+    stage_query<F32>(qv, ld16, nch, sq);
+    __syncthreads();
+    const float l2_bias = l2 ? (1.f - q_sqnorm[0]) : 0.f;
+
+    WarpList<KPL> list;
+    list.clear();
+    uint64_t thr = 0;
+
+    const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
+    const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
+
+    auto consume = [&](const int64_t (&rid)[K1_R], const bool (&va)[K1_R]) {
+        const uint4* rp[K1_R];
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) rp[r] = rows + rid[r] * (int64_t)ld16;
+        float acc[K1_R];
+        rows_dot<F32>(rp, va, ld16, nch, sq, lane, acc);
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) {
+            if (va[r]) {
+                float s = acc[r];
+                if (l2) s = fmaf(2.f, s, l2_bias - row_sqnorm[rid[r]]);
+                const uint64_t key = make_key(s, (uint32_t)rid[r]);
+                if (key > thr) {
+                    list.insert(key, lane);
+                    thr = list.at(k - 1);
+                }
+            }
+        }
+    };
+
+    if (!HAS_MASK) {
+        const int64_t n_groups = (n_rows + K1_R - 1) / K1_R;
+        for (int64_t g = gw; g < n_groups; g += tw) {
+            int64_t rid[K1_R];
+            bool va[K1_R];
+#pragma unroll
+            for (int r = 0; r < K1_R; ++r) {
+                rid[r] = g * K1_R + r;
+                va[r] = rid[r] < n_rows;
+                if (!va[r]) rid[r] = 0;
+            }
+            consume(rid, va);
+        }
+    } else {
+        const int64_t n_groups = (n_rows + 63) / 64;
+        const uint2* mask2 = reinterpret_cast<const uint2*>(mask);
+        for (int64_t g = gw; g < n_groups; g += tw) {
+            const uint2 mw = mask2[g];
+            uint64_t m = ((uint64_t)mw.y << 32) | mw.x;
+            while (m) {
+                int64_t rid[K1_R];
+                bool va[K1_R];
+#pragma unroll
+                for (int r = 0; r < K1_R; ++r) {
+                    va[r] = (m != 0);
+                    rid[r] = 0;
+                    if (va[r]) {
+                        rid[r] = g * 64 + (__ffsll((long long)m) - 1);
+                        m &= m - 1;
+                        va[r] = rid[r] < n_rows;
+                        if (!va[r]) rid[r] = 0;
+                    }
+                }
+                consume(rid, va);
+            }
+        }
+    }
+
+    // ---- CTA merge: every warp's first k entries → shared → bitonic → first k to global
+    __syncthreads();  // query no longer needed; shared memory is reused for keys
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
+    const int kp = next_pow2(k);  // ≤ 32*KPL
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+        const int e = s * 32 + lane;
+        if (e < kp) sk[warp * kp + e] = (e < k) ? list.v[s] : 0ull;
+    }
+    block_bitonic_desc(sk, K1_WARPS * kp, BetterU64());
+    for (int i = threadIdx.x; i < k; i += blockDim.x) part_keys[(int64_t)blockIdx.x * k + i] = sk[i];
+}
+
+// ---- K6a: plain scores (any k): score of every row for one query; masked-out rows get key-0
+// semantics downstream by writing -inf-like NaN pattern?  No: they are written as -INFINITY and
+// the select step also receives the mask.
+template <bool F32, bool HAS_MASK>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+    k6_scores(const uint4* __restrict__ rows, int64_t n_rows, int ld16, int nch, const uint4* __restrict__ qv,
+              const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm, int l2,
+              const uint32_t* __restrict__ mask, float* __restrict__ scores) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* sq = reinterpret_cast<float4*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    stage_query<F32>(qv, ld16, nch, sq);
+    __syncthreads();
+    const float l2_bias = l2 ? (1.f - q_sqnorm[0]) : 0.f;
+    const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
+    const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
+    const int64_t n_groups = (n_rows + K1_R - 1) / K1_R;
+    for (int64_t g = gw; g < n_groups; g += tw) {
+        int64_t rid[K1_R];
+        bool va[K1_R];
+        const uint4* rp[K1_R];
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) {
+            rid[r] = g * K1_R + r;
+            va[r] = rid[r] < n_rows;
+            if (va[r] && HAS_MASK) va[r] = (mask[rid[r] >> 5] >> (rid[r] & 31)) & 1u;
+            rp[r] = rows + (va[r] ? rid[r] : 0) * (int64_t)ld16;
+        }
+        float acc[K1_R];
+        rows_dot<F32>(rp, va, ld16, nch, sq, lane, acc);
+        if (lane < K1_R) {
+            float s = -INFINITY;
+            int64_t row = g * K1_R + lane;
+#pragma unroll
+            for (int r = 0; r < K1_R; ++r)
+                if (lane == r && va[r]) s = l2 ? fmaf(2.f, acc[r], l2_bias - row_sqnorm[rid[r]]) : acc[r];
+            if (row < n_rows) scores[row] = s;
+        }
+    }
+}
+
+static size_t k1_smem_bytes(int dtype, int nch, int k) {
+    size_t q = (size_t)nch * 32 * (dtype == 1 ? 1 : 2) * sizeof(float4);
+    size_t m = (size_t)K1_WARPS * next_pow2(k) * sizeof(uint64_t);
+    return q > m ? q : m;
+}
+
+template <bool F32, int KPL, bool HAS_MASK>
+static cudaError_t k1_launch_t(const void* rows, int64_t n_rows, int ld16, int nch, const void* q,
+                               const float* q_sqnorm, const float* row_sqnorm, int l2, const uint32_t* mask, int k,
+                               uint64_t* part_keys, int grid, size_t smem, cudaStream_t st) {
+    auto kern = k1_scan_topk<F32, KPL, HAS_MASK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, K1_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(rows), n_rows, ld16, nch,
+                                          reinterpret_cast<const uint4*>(q), q_sqnorm, row_sqnorm, l2, mask, k,
+                                          part_keys);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
+                      const float* q_sqnorm, const float* row_sqnorm, int metric, const uint32_t* mask, int k,
+                      uint64_t* part_keys, int sm_count, cudaStream_t st) {
+    (void)dim;
+    if (k < 1 || k > 128) return cudaErrorInvalidValue;
+    const int ld16 = ld * elem_size(dtype) / 16;
+    const int nch = (ld16 + 31) / 32;
+    const int grid = k1_parts(sm_count);
+    const size_t smem = k1_smem_bytes(dtype, nch, k);
+    const int l2 = (metric == 2);
+    const bool f32 = (dtype == 1), big = (k > 32), hm = (mask != nullptr);
+#define YRB_K1(F, K, M) \
+    return k1_launch_t<F, K, M>(rows, n_rows, ld16, nch, q, q_sqnorm, row_sqnorm, l2, mask, k, part_keys, grid, smem, st)
+    if (!f32 && !big && !hm) YRB_K1(false, 1, false);
+    if (!f32 && !big && hm) YRB_K1(false, 1, true);
+    if (!f32 && big && !hm) YRB_K1(false, 4, false);
+    if (!f32 && big && hm) YRB_K1(false, 4, true);
+    if (f32 && !big && !hm) YRB_K1(true, 1, false);
+    if (f32 && !big && hm) YRB_K1(true, 1, true);
+    if (f32 && big && !hm) YRB_K1(true, 4, false);
+    YRB_K1(true, 4, true);
+#undef YRB_K1
+}
+
+cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
+                          const float* q_sqnorm, const float* row_sqnorm, int metric, const uint32_t* mask,
+                          float* scores, int sm_count, cudaStream_t st) {
+    (void)dim;
+    const int ld16 = ld * elem_size(dtype) / 16;
+    const int nch = (ld16 + 31) / 32;
+    const size_t smem = (size_t)nch * 32 * (dtype == 1 ? 1 : 2) * sizeof(float4);
+    const int l2 = (metric == 2);
+    const uint4* r4 = reinterpret_cast<const uint4*>(rows);
+    const uint4* q4 = reinterpret_cast<const uint4*>(q);
+#define YRB_K6(F, M)                                                                                         \
+    {                                                                                                        \
+        auto kern = k6_scores<F, M>;                                                                         \
+        if (smem > 48 * 1024) {                                                                              \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return e;                                                                  \
+        }                                                                                                    \
+        kern<<<sm_count, K1_THREADS, smem, st>>>(r4, n_rows, ld16, nch, q4, q_sqnorm, row_sqnorm, l2, mask,  \
+                                                 scores);                                                    \
+        return cudaGetLastError();                                                                           \
+    }
+    if (dtype == 1) {
+        if (mask) YRB_K6(true, true) else YRB_K6(true, false)
+    } else {
+        if (mask) YRB_K6(false, true) else YRB_K6(false, false)
+    }
+#undef YRB_K6
+}
+
+}  // namespace yrb

@@ -1,0 +1,21 @@
+// k2_batched.h — host interface of K2 (batched tcgen05 GEMM + fused top-k epilogue).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace yrb {
+
+struct K2State;  // cached TMA descriptors + candidate buffers of one index
+K2State* k2_create();
+void k2_destroy(K2State* s);
+void k2_invalidate(K2State* s);  // corpus pointer / capacity changed
+int k2_parts(int sm_count);      // sorted k-lists K2 leaves per query before K3
+bool k2_supported(int dtype, int dim, int k);
+// q: prepared bf16 queries [nq, ld].  Writes nq*k keys (descending) to out_keys.  Returns YRB_* code.
+int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
+              int k, const uint32_t* mask, int metric, const float* q_sqnorm, const float* row_sqnorm,
+              uint64_t* out_keys, uint64_t* scratch, int sm_count, cudaStream_t st, int* launches, std::string& err);
+
+}  // namespace yrb

@@ -1,0 +1,82 @@
+// kernels.h — host-side launchers of the hot-path kernels (internal to libyrb200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yrb {
+
+struct DeviceInfo {
+    int device = 0;
+    int sm_count = 148;
+};
+
+// leading dimension (elements) of stored rows: rows are padded to a multiple of 128 bytes
+inline int row_ld(int dim, int dtype /*0 bf16, 1 f32*/) {
+    int q = dtype == 0 ? 64 : 32;
+    return (dim + q - 1) / q * q;
+}
+inline int elem_size(int dtype) { return dtype == 0 ? 2 : 4; }
+
+// ---- K5: ingest.  src fp32 [n, dim] (device) → dst rows [n, ld] in storage dtype; cosine rows are
+// L2-normalised with an fp64 norm.  sqnorm[n] = ||stored row||^2 in fp32 (used by euclidean).
+cudaError_t launch_ingest(const float* src, int64_t n, int dim, int ld, int metric, int dtype,
+                          void* dst, float* sqnorm, cudaStream_t st);
+
+// ---- K1: single-query scan + in-register top-k.  q = ONE prepared query [ld] in storage dtype.
+// part_keys must hold k1_parts(sm) * k keys.  Writes per-CTA sorted top-k lists.
+int k1_parts(int sm_count);
+cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
+                      const float* q_sqnorm /*device, 1 float*/, const float* row_sqnorm, int metric,
+                      const uint32_t* mask, int k, uint64_t* part_keys, int sm_count,
+                      cudaStream_t st);
+
+// ---- K3: merge `parts` sorted k-lists per query ([parts][nq][k]) into [nq][k] (descending keys).
+// scratch must hold parts*nq*k keys when parts*k > 4096 (multi-pass).
+cudaError_t launch_merge_keys(const uint64_t* in, int parts, int nq, int k, uint64_t* out,
+                              uint64_t* scratch, cudaStream_t st);
+// keys [nq][k] → ids / scores / counts
+cudaError_t launch_decode(const uint64_t* keys, int nq, int k, int64_t* ids, float* scores,
+                          int32_t* counts, cudaStream_t st);
+// cross-rank merge: [parts][nq][k] local keys + row_base[parts] → global ids (score desc, id asc)
+cudaError_t launch_merge_global(const uint64_t* in, int parts, int nq, int k,
+                                const int64_t* row_base, int64_t* ids, float* scores,
+                                int32_t* counts, cudaStream_t st);
+
+// ---- K4: where-program evaluation → bitmask
+struct WhereLeafDev {
+    const void* values;
+    const uint32_t* present;  // bitmask, never NULL for col >= 0
+    int32_t col_type;         // YRB_COL_*, -1 = absent column
+    int32_t op;
+    int32_t operand_begin;
+    int32_t operand_count;
+};
+struct WhereProgDev {
+    int32_t n_leaves;
+    int32_t n_postfix;
+    WhereLeafDev leaves[64];
+    int64_t operands[256];
+    int32_t postfix[160];
+};
+// prog: device copy of WhereProgDev.  live / extra may be NULL.  out_mask: ceil(n/32) words,
+// padded words up to an even count are zeroed.  pass_count: device int64, accumulated (+=).
+cudaError_t launch_where(const WhereProgDev* prog, int64_t n_rows, const uint32_t* live,
+                         const uint32_t* extra, uint32_t* out_mask, unsigned long long* pass_count,
+                         cudaStream_t st);
+cudaError_t launch_mask_and(const uint32_t* a, const uint32_t* b, int64_t n_words, uint32_t* out,
+                            cudaStream_t st);
+
+// ---- K6: any-k path.  scores fp32 [n_rows] for one query + radix select of the top k.
+cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
+                          const float* q_sqnorm, const float* row_sqnorm, int metric,
+                          const uint32_t* mask, float* scores, int sm_count, cudaStream_t st);
+size_t select_scratch_bytes(int64_t n_rows, int k);
+cudaError_t launch_select(const float* scores, int64_t n_rows, int k, uint64_t* out_keys,
+                          void* scratch, int sm_count, cudaStream_t st);
+
+// ---- K2: batched tcgen05 GEMM + fused top-k epilogue (bf16 storage only).
+
+
+
+}  // namespace yrb

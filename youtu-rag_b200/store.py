@@ -1,0 +1,225 @@
+"""B200VectorStore — the drop-in `BaseVectorStore` whose search runs on hand-written sm_100a CUDA.
+
+Interface parity target: ChromaVectorStore (utu/rag/storage/implementations/chroma_store.py), the
+store every agent path constructs today.  Method by method:
+
+  add_chunks            chroma_store.py:64-88    flattened metadata rows, embeddings → device (K5)
+  search                chroma_store.py:90-148   filters normalisation :104-116, exact top-k instead of
+                                                 HNSW, score = 1 - distance :132-135, Chunk shaping :137-146
+  delete                chroma_store.py:150-160  tombstones
+  delete_by_document_id chroma_store.py:162-183
+  delete_by_metadata    chroma_store.py:185-222  (multi-key dict → $and :196-203, errors → 0 :220-222)
+  get_by_id             chroma_store.py:224-247
+  count / clear         chroma_store.py:249-272
+
+The Python side keeps only what has no arithmetic: row → (chunk id, text, metadata dict) tables and
+the columnar metadata mirror; all scoring, filtering and selection happen behind include/yrb200.h.
+There is no CPU search path: without libyrb200.so or a B200 the constructor/first add raises.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Any
+
+import numpy as np
+
+from . import native
+from .base import BaseVectorStore, Chunk
+from .config import VectorStoreConfig
+from .metadata import MetadataTable
+from .where import compile_where, normalize_filters
+
+logger = logging.getLogger(__name__)
+
+_METRIC_NAMES = ("cosine", "euclidean", "dot")
+
+
+class B200VectorStore(BaseVectorStore):
+    """Exact dense retrieval over a device-resident chunk-embedding matrix."""
+
+    def __init__(self, config: VectorStoreConfig):
+        self.config = config
+        p = dict(getattr(config, "index_params", None) or {})
+        self._dtype = p.get("storage_dtype", "bf16")
+        if self._dtype not in native.DTYPES:
+            raise ValueError(f"index_params.storage_dtype must be one of {sorted(native.DTYPES)}, got {self._dtype!r}")
+        self._device = int(p.get("device", 0))
+        self._reserve = int(p.get("reserve_rows", 0))
+        self._include_embeddings = bool(p.get("include_embeddings", False))
+        # unknown metric names fall back to cosine like chroma_store.py:52
+        metric = config.distance_metric if config.distance_metric in _METRIC_NAMES else "cosine"
+        self._metric = metric
+        native.lib()  # fail now, loudly, if the CUDA extension was not built
+        self._index: native.Index | None = None
+        self._ids: list[str | None] = []
+        self._documents: list[str | None] = []
+        self._metadatas: list[dict[str, Any] | None] = []
+        self._row_of: dict[str, int] = {}
+        self._meta = MetadataTable()
+        logger.info("Initialized B200 vector store (collection %s, metric %s, storage %s, device %d)",
+                    config.collection_name, metric, self._dtype, self._device)
+
+    # ------------------------------------------------------------------ helpers
+    def _ensure_index(self, dim: int) -> native.Index:
+        if self._index is None:
+            self._index = native.Index(dim, self._metric, self._dtype, self._device, self._reserve)
+        elif self._index.dim != dim:
+            raise ValueError(f"Embedding dimension {dim} does not match collection dimensionality {self._index.dim}")
+        return self._index
+
+    def _make_chunk(self, row: int, embedding: list[float] | None) -> Chunk:
+        meta = dict(self._metadatas[row] or {})
+        return Chunk(id=self._ids[row], document_id=meta.get("document_id", ""), content=self._documents[row],
+                     chunk_index=meta.get("chunk_index", 0), metadata=meta, embedding=embedding)
+
+    def _compile(self, filters: dict[str, Any] | None):
+        where = normalize_filters(filters)
+        compiled, cols = compile_where(where, self._meta)
+        if cols:
+            self._meta.sync(self._index, cols)
+        return compiled
+
+    def _rows_matching(self, where: dict[str, Any]) -> list[int]:
+        """collection.get(where=…) stand-in: rows (live) passing a where clause, via K4."""
+        if self._index is None or self._index.rows == 0:
+            return []
+        compiled, cols = compile_where(where, self._meta)
+        if cols:
+            self._meta.sync(self._index, cols)
+        words, n = self._index.where_mask(compiled)
+        if n == 0:
+            return []
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")[: self._index.rows]
+        return np.flatnonzero(bits).tolist()
+
+    # ------------------------------------------------------------------ BaseVectorStore
+    async def add_chunks(self, chunks: list[Chunk]) -> None:
+        if not chunks:
+            return
+        seen: set[str] = set()
+        for c in chunks:
+            if c.id in seen:
+                raise ValueError(f"Expected IDs to be unique, found duplicates of: {c.id}")
+            seen.add(c.id)
+            if c.embedding is None:
+                raise ValueError(f"Chunk {c.id} has no embedding")
+        fresh = [c for c in chunks if c.id not in self._row_of]
+        if len(fresh) != len(chunks):
+            # Chroma's add() leaves existing ids untouched
+            logger.warning("Add of %d existing chunk ids ignored", len(chunks) - len(fresh))
+        if not fresh:
+            return
+        emb = np.asarray([c.embedding for c in fresh], dtype=np.float32)
+        if emb.ndim != 2:
+            raise ValueError("Expected every embedding to have the same dimension")
+        if not np.isfinite(emb).all():
+            raise ValueError("Embeddings contain NaN or infinite values")
+        metas = []
+        for c in fresh:
+            m = {"document_id": c.document_id, "chunk_index": c.chunk_index,
+                 **{k: v for k, v in (c.metadata or {}).items() if v is not None}}
+            MetadataTable.validate(m)
+            metas.append(m)
+        index = self._ensure_index(emb.shape[1])
+        base = index.rows
+        assert base == len(self._ids) == self._meta.rows
+        index.append(emb)
+        for i, c in enumerate(fresh):
+            self._row_of[c.id] = base + i
+        self._ids.extend(c.id for c in fresh)
+        self._documents.extend(c.content for c in fresh)
+        self._metadatas.extend(metas)
+        self._meta.append(metas)
+        logger.info("Added %d chunks to B200 index", len(fresh))
+
+    async def search(self, query_embedding: list[float], top_k: int = 5,
+                     filters: dict[str, Any] | None = None) -> list[tuple[Chunk, float]]:
+        out = await self.search_batch([query_embedding], top_k=top_k, filters=filters)
+        return out[0]
+
+    async def search_batch(self, query_embeddings, top_k: int = 5,
+                           filters: dict[str, Any] | None = None) -> list[list[tuple[Chunk, float]]]:
+        """Q queries in one device pass (the batched entry point VectorRetriever.batch_retrieve uses;
+        the reference loops single searches, base_retriever.py:95-99)."""
+        q = np.asarray(query_embeddings, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if top_k < 1:
+            raise ValueError(f"Expected n_results to be a positive integer, got {top_k}")
+        if not np.isfinite(q).all():
+            raise ValueError("Query embedding contains NaN or infinite values")
+        if self._index is None or self._index.counts()[1] == 0:
+            compile_where(normalize_filters(filters), self._meta)  # still validate like Chroma would
+            return [[] for _ in range(q.shape[0])]
+        if q.shape[1] != self._index.dim:
+            raise ValueError(
+                f"Embedding dimension {q.shape[1]} does not match collection dimensionality {self._index.dim}")
+        compiled = self._compile(filters)
+        ids, scores, counts = self._index.search(q, int(top_k), where=compiled)
+        results = []
+        for j in range(q.shape[0]):
+            n = int(counts[j])
+            rows = ids[j, :n]
+            embs = self._index.read_rows(rows).tolist() if (self._include_embeddings and n) else [None] * n
+            results.append([(self._make_chunk(int(rows[i]), embs[i]), float(scores[j, i])) for i in range(n)])
+        return results
+
+    async def delete(self, chunk_ids: list[str]) -> None:
+        if not chunk_ids:
+            return
+        rows = [self._row_of.pop(cid) for cid in chunk_ids if cid in self._row_of]
+        if rows:
+            self._index.set_live(rows, False)
+            for r in rows:
+                self._ids[r] = self._documents[r] = self._metadatas[r] = None
+        logger.info("Deleted %d chunks from B200 index", len(rows))
+
+    async def delete_by_document_id(self, document_id: str) -> int:
+        rows = self._rows_matching({"document_id": document_id})
+        if not rows:
+            logger.info("No chunks found for document_id: %s", document_id)
+            return 0
+        await self.delete([self._ids[r] for r in rows])
+        return len(rows)
+
+    async def delete_by_metadata(self, metadata_filter: dict[str, Any]) -> int:
+        if len(metadata_filter) > 1:
+            where = {"$and": [{k: v} for k, v in metadata_filter.items()]}
+        else:
+            where = metadata_filter
+        try:
+            rows = self._rows_matching(where)
+            if not rows:
+                return 0
+            await self.delete([self._ids[r] for r in rows])
+            return len(rows)
+        except Exception as e:  # noqa: BLE001 - chroma_store.py:220-222 logs and returns 0
+            logger.error("Failed to delete by metadata %s: %s", metadata_filter, e)
+            return 0
+
+    async def get_by_id(self, chunk_id: str) -> Chunk | None:
+        row = self._row_of.get(chunk_id)
+        if row is None:
+            return None
+        return self._make_chunk(row, self._index.read_rows([row])[0].tolist())
+
+    async def count(self) -> int:
+        return len(self._row_of)
+
+    async def clear(self) -> None:
+        if self._index is not None:
+            self._index.clear()
+        self._ids, self._documents, self._metadatas, self._row_of = [], [], [], {}
+        self._meta.clear()
+        logger.info("Cleared B200 collection: %s", self.config.collection_name)
+
+    # ------------------------------------------------------------------ extras
+    def close(self) -> None:
+        if self._index is not None:
+            self._index.close()
+            self._index = None
+
+    @property
+    def index(self) -> native.Index | None:
+        return self._index
