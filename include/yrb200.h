@@ -158,6 +158,11 @@ YRB_API int yrb_index_set_path(yrb_index* ix, int path);
 /* launches issued by this index since creation (bench `gpu_launches`), and the duration in ms of
  * the dominant kernel of the last search measured with CUDA events when enabled. */
 YRB_API int yrb_index_stats(const yrb_index* ix, int64_t* out_kernel_launches);
+/* CUDA-event timing of the dominant kernel (K1 scan / K2 GEMM) of every search issued while
+ * enabled: events are recorded on the launching stream around that kernel only.  read() waits for
+ * the recorded events, returns the summed duration and launch count since the last read, resets. */
+YRB_API int yrb_index_profile(yrb_index* ix, int enable);
+YRB_API int yrb_index_profile_read(yrb_index* ix, double* out_total_ms, int64_t* out_launches);
 
 /* selection key = (monotone(score) << 32) | ~row : larger key = better (score desc, row asc) */
 static inline uint32_t yrb_key_row(uint64_t key) { return ~(uint32_t)(key & 0xffffffffu); }

@@ -1,0 +1,119 @@
+"""B200VectorStore (the drop-in BaseVectorStore) against outputs of the reference's own glue and
+against the oracle store.  Needs a B200."""
+
+import asyncio
+
+import numpy as np
+import pytest
+
+from tests.golden_util import GOLDEN, compare_with_golden, golden_chunks
+from tests.oracle_store import OracleStore
+from youtu_rag_b200 import (B200VectorStore, RetrieverConfig, VectorRetriever, VectorStoreConfig, VectorStoreFactory)
+from youtu_rag_b200.base import BaseEmbedder
+
+pytestmark = pytest.mark.gpu
+
+
+def run(c):
+    return asyncio.run(c)
+
+
+def make(metric, dtype):
+    cfg = VectorStoreConfig(backend="b200", collection_name="t", distance_metric=metric,
+                            index_params={"storage_dtype": dtype})
+    s = VectorStoreFactory.create(cfg)
+    assert isinstance(s, B200VectorStore) and s.config.backend == "b200"
+    run(s.add_chunks(golden_chunks()))
+    return s
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+def test_store_reproduces_reference_glue_f32(metric):
+    s = make(metric, "f32")
+    for rec in GOLDEN["chroma"]:
+        if rec["metric"] != metric:
+            continue
+        q = GOLDEN["queries"][rec["query"]]
+        if "error" in rec:
+            with pytest.raises(ValueError):
+                run(s.search(q, rec["top_k"], rec["filters"]))
+        else:
+            compare_with_golden(run(s.search(q, rec["top_k"], rec["filters"])), rec["results"], tol=1e-5)
+
+
+def test_store_bf16_within_north_star_tolerance():
+    s = make("cosine", "bf16")
+    o = OracleStore("cosine", "bf16")
+    run(o.add_chunks(golden_chunks()))
+    for rec in GOLDEN["chroma"]:
+        if rec["metric"] != "cosine" or "error" in rec:
+            continue
+        q = GOLDEN["queries"][rec["query"]]
+        got = run(s.search(q, rec["top_k"], rec["filters"]))
+        want = run(o.search(q, rec["top_k"], rec["filters"]))
+        # same stored bf16 operands on both sides → ids identical up to exact ties
+        compare_with_golden(got, [{"id": c.id, "score": sc} for c, sc in want], tol=1e-5)
+        # and within 1e-3 of the fp32 reference scores
+        ref = {w["id"]: w["score"] for w in rec["results"]}
+        for c, sc in got:
+            if c.id in ref:
+                assert abs(sc - ref[c.id]) <= 1e-3 * max(1.0, abs(ref[c.id])) + 2e-3
+
+
+def test_store_mutations_match_reference_glue():
+    s = make("cosine", "f32")
+    mut = GOLDEN["chroma_mutations"]
+    assert run(s.count()) == mut["count0"]
+    assert run(s.delete_by_document_id("doc2")) == mut["deleted_doc2"]
+    assert run(s.delete_by_metadata({"source": "file1.pdf", "index_type": "index_summary"})) == mut["deleted_meta"]
+    run(s.delete(["doc0_chunk_0", "nope"]))
+    assert run(s.count()) == mut["count1"]
+    g = run(s.get_by_id("doc0_chunk_2"))
+    assert {"id": g.id, "document_id": g.document_id, "chunk_index": g.chunk_index, "metadata": g.metadata} == mut["get"]
+    emb = np.asarray(GOLDEN["corpus"]["embeddings"][2], np.float32)
+    np.testing.assert_allclose(g.embedding, emb / np.linalg.norm(emb), atol=1e-6)
+    assert run(s.get_by_id("doc0_chunk_0")) is None
+    compare_with_golden(run(s.search(GOLDEN["queries"][0], top_k=5)), mut["search_after"], tol=1e-5)
+    run(s.clear())
+    assert run(s.count()) == mut["count2"] and run(s.search(GOLDEN["queries"][0], top_k=5)) == []
+    run(s.add_chunks(golden_chunks()[:10]))            # usable again after clear
+    assert run(s.count()) == 10 and len(run(s.search(GOLDEN["queries"][0], top_k=3))) == 3
+
+
+def test_store_edge_cases():
+    s = B200VectorStore(VectorStoreConfig(collection_name="e"))
+    assert run(s.search([0.0] * 8, 3)) == [] and run(s.count()) == 0
+    run(s.add_chunks([]))
+    ch = golden_chunks()
+    run(s.add_chunks(ch[:5]))
+    run(s.add_chunks(ch[:7]))                           # existing ids ignored, new ones added
+    assert run(s.count()) == 7
+    with pytest.raises(ValueError):
+        run(s.add_chunks([ch[9], ch[9]]))
+    with pytest.raises(ValueError):
+        run(s.search([0.0] * 3, 3))                     # wrong dimension
+    with pytest.raises(ValueError):
+        run(s.search(GOLDEN["queries"][0], 0))
+    res = run(s.search(GOLDEN["queries"][0], 50))       # k > count
+    assert len(res) == 7
+    zero = run(s.search([0.0] * 16, 2))                 # zero query: all cosine scores 0, ids by row order
+    assert [c.id for c, _ in zero] == [ch[0].id, ch[1].id] and all(sc == 0.0 for _, sc in zero)
+
+
+class _Emb(BaseEmbedder):
+    async def embed_texts(self, texts):
+        return [GOLDEN["queries"][int(t)] for t in texts]
+
+    async def embed_query(self, query):
+        return GOLDEN["queries"][int(query)]
+
+
+def test_retriever_over_b200_store_matches_reference_retriever():
+    s = make("cosine", "f32")
+    for rec in GOLDEN["retriever"]:
+        r = VectorRetriever(s, _Emb(), RetrieverConfig(top_k=4, similarity_threshold=rec["config_threshold"]))
+        single = run(r.retrieve("1", **rec["kwargs"]))
+        batch = run(r.batch_retrieve(["0", "1", "2"], top_k=3, **rec["kwargs"]))
+        for got, want in [(single, rec["single"])] + list(zip(batch, rec["batch"])):
+            assert [x.rank for x in got] == [w["rank"] for w in want]
+            compare_with_golden([(x.chunk, x.score) for x in got], want, tol=1e-5)

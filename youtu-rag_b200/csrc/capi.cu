@@ -89,6 +89,11 @@ struct yrb_index {
     yrb::K2State* k2 = nullptr;
     int path = 0;
     int64_t launches = 0;
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+    size_t prof_used = 0;
+    double prof_ms = 0.0;
+    int64_t prof_n = 0;
     std::mutex mu;
 };
 
@@ -293,6 +298,36 @@ int resolve_mask(yrb_index* ix, const yrb_where* w, const uint32_t* dev_extra, c
     return YRB_OK;
 }
 
+int prof_flush(yrb_index* ix) {
+    for (size_t i = 0; i + 1 < ix->prof_used; i += 2) {
+        CK(cudaEventSynchronize(ix->prof_ev[i + 1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ix->prof_ev[i], ix->prof_ev[i + 1]));
+        ix->prof_ms += ms;
+        ix->prof_n++;
+    }
+    ix->prof_used = 0;
+    return YRB_OK;
+}
+
+int prof_mark(yrb_index* ix, cudaStream_t st) {
+    if (!ix->prof) return YRB_OK;
+    if (ix->prof_used == ix->prof_ev.size()) {
+        if (ix->prof_ev.size() >= 8192) {
+            int rc = prof_flush(ix);
+            if (rc) return rc;
+        } else {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            ix->prof_ev.push_back(a);
+            ix->prof_ev.push_back(b);
+        }
+    }
+    CK(cudaEventRecord(ix->prof_ev[ix->prof_used++], st));
+    return YRB_OK;
+}
+
 // queries already prepared in ix->d_q / ix->d_qsq; writes nq*k keys
 int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* out_keys, cudaStream_t st) {
     int path = ix->path;
@@ -308,19 +343,25 @@ int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* ou
     const size_t es = yrb::elem_size(ix->dtype);
     if (path == 2) {
         int launches = 0;
-        int rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
+        int rc = prof_mark(ix, st);
+        if (rc) return rc;
+        rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
                                 ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ix->d_mscratch, ix->sm_count, st,
                                 &launches, g_err);
         ix->launches += launches;
+        if (!rc) rc = prof_mark(ix, st);
         return rc;
     }
     if (path == 1) {
         const int parts = yrb::k1_parts(ix->sm_count);
         for (int j = 0; j < nq; ++j) {
             uint64_t* pk = ix->d_parts + (size_t)j * parts * k;
+            int rc = prof_mark(ix, st);
+            if (rc) return rc;
             CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld,
                               reinterpret_cast<const char*>(ix->d_q) + (size_t)j * ix->ld * es, ix->d_qsq + j,
                               ix->d_sqnorm, ix->metric, mask, k, pk, ix->sm_count, st));
+            if ((rc = prof_mark(ix, st))) return rc;
             CK(yrb::launch_merge_keys(pk, parts, 1, k, out_keys + (size_t)j * k, ix->d_mscratch, st));
             ix->launches += 2;
         }
@@ -449,6 +490,7 @@ int yrb_index_destroy(yrb_index* ix) {
         FREE_DEV(kv.second.present);
     }
     if (ix->k2) yrb::k2_destroy(ix->k2);
+    for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
     return YRB_OK;
@@ -772,6 +814,26 @@ int yrb_index_set_path(yrb_index* ix, int path) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (path < 0 || path > 3) return fail(YRB_ERR_INVALID, "path must be 0..3");
     ix->path = path;
+    return YRB_OK;
+}
+
+int yrb_index_profile(yrb_index* ix, int enable) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->prof = enable != 0;
+    return YRB_OK;
+}
+
+int yrb_index_profile_read(yrb_index* ix, double* out_total_ms, int64_t* out_launches) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if ((rc = prof_flush(ix))) return rc;
+    if (out_total_ms) *out_total_ms = ix->prof_ms;
+    if (out_launches) *out_launches = ix->prof_n;
+    ix->prof_ms = 0.0;
+    ix->prof_n = 0;
     return YRB_OK;
 }
 

@@ -32,7 +32,8 @@ EXPORTS = (
     "yrb_index_reserve", "yrb_index_count", "yrb_index_info", "yrb_index_append_host_f32",
     "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_set_live", "yrb_index_clear",
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_device",
-    "yrb_merge_topk_device", "yrb_index_set_path", "yrb_index_stats",
+    "yrb_merge_topk_device", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
+    "yrb_index_profile_read",
 )
 
 
@@ -88,6 +89,8 @@ def lib() -> C.CDLL:
     L.yrb_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_index_set_path.argtypes = [vp, i32]
     L.yrb_index_stats.argtypes = [vp, C.POINTER(i64)]
+    L.yrb_index_profile.argtypes = [vp, i32]
+    L.yrb_index_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("yrb_last_error",):
@@ -226,6 +229,15 @@ class Index:
 
     def set_path(self, path: int) -> None:
         _ck(lib().yrb_index_set_path(self._h, path))
+
+    def profile(self, enable: bool) -> None:
+        _ck(lib().yrb_index_profile(self._h, int(enable)))
+
+    def profile_read(self) -> tuple[float, int]:
+        """(summed ms, launches) of the dominant kernel since the last read (CUDA events)."""
+        ms, n = C.c_double(), C.c_int64()
+        _ck(lib().yrb_index_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launches(self) -> int:
         n = C.c_int64()

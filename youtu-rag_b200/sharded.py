@@ -1,0 +1,112 @@
+"""Row-sharded search across the GPUs of one box: one process per GPU (torch.distributed / NCCL).
+
+Rank r holds the contiguous rows [row_base[r], row_base[r+1]) of the collection.  A search is
+(1) the local scan + top-k on every rank (K1/K2), (2) ONE all-gather of the nq·k selection keys
+(8 bytes each) over NVLink, (3) kernel K3 (`yrb_merge_topk_device`) merging the world·k candidates
+per query with the global (score desc, id asc) rule — on every rank, so any rank can answer.
+The reference has no counterpart (a single Chroma collection in one process,
+utu/rag/storage/implementations/chroma_store.py:41-59); SURVEY.md §8e defines this exchange.
+
+PyTorch here is plumbing only: tensor ownership of the exchange buffers, the current CUDA stream
+and the process group.  With the `gloo` backend (CPU tests) the exchange is exercised on host
+tensors and the merge runs through `merge_host`, a test-only stand-in for K3.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import native
+
+
+def shard_bounds(n_rows: int, world: int) -> list[int]:
+    """row_base[0..world]: contiguous shards, the first n_rows % world ranks get one extra row."""
+    base, rem = divmod(n_rows, world)
+    out = [0]
+    for r in range(world):
+        out.append(out[-1] + base + (1 if r < rem else 0))
+    return out
+
+
+class ShardedSearcher:
+    def __init__(self, index: native.Index | None, row_base: list[int], group=None):
+        self.index = index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        assert len(row_base) == self.world + 1
+        self.row_base = list(row_base)
+        self._cuda = index is not None
+        if self._cuda:
+            self.device = torch.device("cuda", index.device)
+            self._base_dev = torch.tensor(self.row_base[:-1], dtype=torch.int64, device=self.device)
+        self._bufs = {}
+
+    def _buffers(self, nq: int, k: int):
+        key = (nq, k)
+        if key not in self._bufs:
+            dev = self.device
+            self._bufs[key] = dict(
+                local=torch.zeros(nq * k, dtype=torch.int64, device=dev),
+                gathered=torch.zeros(self.world * nq * k, dtype=torch.int64, device=dev),
+                ids=torch.empty(nq * k, dtype=torch.int64, device=dev),
+                scores=torch.empty(nq * k, dtype=torch.float32, device=dev),
+                counts=torch.empty(nq, dtype=torch.int32, device=dev))
+        return self._bufs[key]
+
+    def search_device(self, dev_queries: torch.Tensor, k: int, dev_mask: torch.Tensor | None = None):
+        """queries fp32 [nq, dim] on this rank's GPU (identical on all ranks).  Returns device tensors
+        (ids [nq,k] global row ids, scores [nq,k], counts [nq]); asynchronous on the current stream."""
+        nq = dev_queries.shape[0]
+        b = self._buffers(nq, k)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self.index.search_device(dev_queries.data_ptr(), nq, k, dev_mask.data_ptr() if dev_mask is not None else 0,
+                                 b["local"].data_ptr(), st)
+        if self.world > 1:
+            dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+            src = b["gathered"]
+        else:
+            src = b["local"]
+        native.merge_topk_device(self.index.device, src.data_ptr(), self.world, nq, k, self._base_dev.data_ptr(),
+                                 b["ids"].data_ptr(), b["scores"].data_ptr(), b["counts"].data_ptr(), st)
+        return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
+
+    def search(self, queries: np.ndarray, k: int, dev_mask: torch.Tensor | None = None):
+        """Host in / host out (pinned staging is torch's)."""
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
+        ids, scores, counts = self.search_device(q, k, dev_mask)
+        return ids.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
+
+
+# ------------------------------------------------------------------ host-side exchange (gloo tests)
+def exchange_host(local_keys: np.ndarray, group=None) -> np.ndarray:
+    """all-gather of one rank's [nq, k] uint64 keys over any backend → [world, nq, k]."""
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(np.ascontiguousarray(local_keys).view(np.int64))
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return np.stack([o.numpy().view(np.uint64) for o in out])
+
+
+def merge_host(gathered: np.ndarray, row_base: list[int], k: int):
+    """What K3 computes, on the host: [world, nq, k] keys → global ids/scores ordered (score desc, id asc).
+    Bookkeeping for CPU tests of the sharding logic; the product path is yrb_merge_topk_device."""
+    world, nq, _ = gathered.shape
+    ids = np.full((nq, k), -1, np.int64)
+    scores = np.full((nq, k), -np.inf, np.float32)
+    counts = np.zeros(nq, np.int32)
+    for q in range(nq):
+        cand = []
+        for p in range(world):
+            rows, sc = native.decode_keys(gathered[p, q])
+            ok = rows >= 0
+            cand += [(-float(s), int(r) + row_base[p], (gathered[p, q][i] >> np.uint64(32))) for i, (r, s) in
+                     enumerate(zip(rows, sc)) if ok[i]]
+        cand.sort(key=lambda t: (-int(t[2]), t[1]))
+        cand = cand[:k]
+        counts[q] = len(cand)
+        for j, (ns, gid, _) in enumerate(cand):
+            ids[q, j], scores[q, j] = gid, -ns
+    return ids, scores, counts
