@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, device: int):
         super().__init__(daemon=True)
         self.device, self.samples, self.reasons, self.max_mhz = device, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         try:
@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
             }
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
                 nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = get_reasons(h)
                 for bit, name in names.items():
@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
     def finish(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -241,7 +241,7 @@ def run_b200(args):
     hq = host_queries(dim, nq)
     dq = torch.from_numpy(hq).to(dev)
     searcher = ShardedSearcher(index, bounds)
-    st = torch.cuda.current_stream(dev)
+    st = searcher.stream  # every kernel of a step is launched on this stream
 
     def step_device(i):
         return searcher.search_device(dq[i % N_QUERY_SETS], k, dev_mask)

@@ -42,6 +42,8 @@ class ShardedSearcher:
         if self._cuda:
             self.device = torch.device("cuda", index.device)
             self._base_dev = torch.tensor(self.row_base[:-1], dtype=torch.int64, device=self.device)
+            # a real (non-NULL) stream: the C ABI treats a NULL stream as "the index's own stream"
+            self.stream = torch.cuda.Stream(self.device)
         self._bufs = {}
 
     def _buffers(self, nq: int, k: int):
@@ -58,26 +60,30 @@ class ShardedSearcher:
 
     def search_device(self, dev_queries: torch.Tensor, k: int, dev_mask: torch.Tensor | None = None):
         """queries fp32 [nq, dim] on this rank's GPU (identical on all ranks).  Returns device tensors
-        (ids [nq,k] global row ids, scores [nq,k], counts [nq]); asynchronous on the current stream."""
+        (ids [nq,k] global row ids, scores [nq,k], counts [nq]); asynchronous on `self.stream` (inputs must
+        be ready before the call; consumers synchronise with `self.stream`)."""
         nq = dev_queries.shape[0]
         b = self._buffers(nq, k)
-        st = torch.cuda.current_stream(self.device).cuda_stream
-        self.index.search_device(dev_queries.data_ptr(), nq, k, dev_mask.data_ptr() if dev_mask is not None else 0,
-                                 b["local"].data_ptr(), st)
-        if self.world > 1:
-            dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
-            src = b["gathered"]
-        else:
-            src = b["local"]
-        native.merge_topk_device(self.index.device, src.data_ptr(), self.world, nq, k, self._base_dev.data_ptr(),
-                                 b["ids"].data_ptr(), b["scores"].data_ptr(), b["counts"].data_ptr(), st)
+        with torch.cuda.stream(self.stream):
+            st = self.stream.cuda_stream
+            self.index.search_device(dev_queries.data_ptr(), nq, k, dev_mask.data_ptr() if dev_mask is not None else 0,
+                                     b["local"].data_ptr(), st)
+            if self.world > 1:
+                dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+                src = b["gathered"]
+            else:
+                src = b["local"]
+            native.merge_topk_device(self.index.device, src.data_ptr(), self.world, nq, k, self._base_dev.data_ptr(),
+                                     b["ids"].data_ptr(), b["scores"].data_ptr(), b["counts"].data_ptr(), st)
         return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
 
     def search(self, queries: np.ndarray, k: int, dev_mask: torch.Tensor | None = None):
         """Host in / host out (pinned staging is torch's)."""
-        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
-        ids, scores, counts = self.search_device(q, k, dev_mask)
-        return ids.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
+        with torch.cuda.stream(self.stream):
+            q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
+            ids, scores, counts = self.search_device(q, k, dev_mask)
+            out = ids.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
+        return out
 
 
 # ------------------------------------------------------------------ host-side exchange (gloo tests)
