@@ -1,0 +1,119 @@
+"""K2 (tcgen05 GEMM + fused top-k) parity with the oracle and with K1, through the C ABI.  Needs a B200."""
+
+import numpy as np
+import pytest
+
+from oracle import exact_search as ox
+from tests.helpers import check_topk, unit_rows
+from youtu_rag_b200 import native
+
+pytestmark = pytest.mark.gpu
+
+
+def build(x, metric="cosine"):
+    ix = native.Index(x.shape[1], metric, "bf16", 0, 0)
+    ix.append(x)
+    return ix
+
+
+@pytest.mark.parametrize("n,d,nq", [(100, 64, 8), (1000, 128, 100), (5000, 768, 128), (20000, 1024, 129),
+                                    (40000, 1024, 256), (33333, 200, 300), (19000, 2048, 16)])
+def test_k2_matches_oracle(n, d, nq):
+    x = unit_rows(n, d, n + d)
+    ix = build(x)
+    ix.set_path(native.PATH_K2)
+    rows = ix.read_rows(np.arange(n))
+    qs = unit_rows(nq, d, 7)
+    for k in (1, 10, 100, 128):
+        ids, scores, counts = ix.search(qs, k)
+        for j in list(range(0, nq, max(1, nq // 9))) + [nq - 1]:
+            c = int(counts[j])
+            assert c == min(k, n)
+            check_topk(ids[j, :c], scores[j, :c], rows, ox.prepare(qs[j], "cosine", "bf16")[0], k, "cosine", "bf16")
+
+
+def test_k2_equals_k1_every_query():
+    n, d, nq, k = 60000, 1024, 256, 100
+    x = unit_rows(n, d, 3)
+    x[[5, 700, 59999]] = x[5]                      # exact ties
+    ix = build(x)
+    qs = unit_rows(nq, d, 4)
+    qs[0] = x[5]
+    ix.set_path(native.PATH_K2)
+    a = ix.search(qs, k)
+    ix.set_path(native.PATH_K1)
+    b = ix.search(qs, k)
+    assert a[0][0, :3].tolist() == [5, 700, 59999]
+    same = (a[0] == b[0]).all(axis=1)
+    # tensor-core and FMA accumulation orders differ: allow swaps only between scores tied to ~1e-6
+    for j in np.flatnonzero(~same):
+        diff = np.flatnonzero(a[0][j] != b[0][j])
+        assert np.abs(a[1][j][diff] - b[1][j][diff]).max() < 3e-6
+    assert same.mean() > 0.9
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-4, atol=3e-6)
+
+
+@pytest.mark.parametrize("sel", [0.0, 0.01, 0.1, 0.9])
+def test_k2_mask(sel):
+    n, d, nq = 30000, 256, 64
+    x = unit_rows(n, d, 5)
+    ix = build(x)
+    ix.set_path(native.PATH_K2)
+    rows = ix.read_rows(np.arange(n))
+    mask = np.random.default_rng(6).random(n) < sel
+    qs = unit_rows(nq, d, 8)
+    ids, scores, counts = ix.search(qs, 10, mask=ox.pack_mask(mask))
+    for j in (0, 31, 63):
+        c = int(counts[j])
+        assert c == min(10, int(mask.sum()))
+        check_topk(ids[j, :c], scores[j, :c], rows, ox.prepare(qs[j], "cosine", "bf16")[0], 10, "cosine", "bf16", mask=mask)
+
+
+def test_k2_dot_metric_and_tombstones():
+    n, d, nq = 10000, 128, 32
+    x = unit_rows(n, d, 9) * np.random.default_rng(1).uniform(0.5, 2, (n, 1)).astype(np.float32)
+    ix = build(x, "dot")
+    ix.set_path(native.PATH_K2)
+    rows = ix.read_rows(np.arange(n))
+    qs = unit_rows(nq, d, 10) * 1.5
+    ids, scores, counts = ix.search(qs, 20)
+    check_topk(ids[3], scores[3], rows, ox.prepare(qs[3], "dot", "bf16")[0], 20, "dot", "bf16")
+    dead = ids[3, :5].tolist()
+    ix.set_live(dead, False)
+    live = np.ones(n, bool); live[dead] = False
+    ids2, scores2, _ = ix.search(qs, 20)
+    check_topk(ids2[3], scores2[3], rows, ox.prepare(qs[3], "dot", "bf16")[0], 20, "dot", "bf16", mask=live)
+
+
+def test_k2_adversarial_order_forces_compaction():
+    """Rows sorted by increasing score for query 0: every later tile beats the threshold, so candidate
+    buffers overflow and the in-kernel compaction path has to be exact."""
+    n, d = 148 * 128 * 6, 64
+    rng = np.random.default_rng(11)
+    q = unit_rows(1, d, 12)[0]
+    noise = unit_rows(n, d, 13)
+    w = np.linspace(-0.9, 0.9, n, dtype=np.float32)[:, None]
+    x = w * q[None, :] + 0.3 * noise
+    ix = build(x)
+    ix.set_path(native.PATH_K2)
+    rows = ix.read_rows(np.arange(n))
+    qs = np.concatenate([q[None], unit_rows(15, d, 14)])
+    ids, scores, counts = ix.search(qs, 100)
+    for j in (0, 1, 15):
+        check_topk(ids[j], scores[j], rows, ox.prepare(qs[j], "cosine", "bf16")[0], 100, "cosine", "bf16")
+
+
+def test_auto_path_uses_k2_for_batches_and_store_batch_api():
+    import asyncio
+
+    from tests.golden_util import GOLDEN, golden_chunks
+    from youtu_rag_b200 import B200VectorStore, VectorStoreConfig
+
+    s = B200VectorStore(VectorStoreConfig(collection_name="b"))
+    asyncio.run(s.add_chunks(golden_chunks()))
+    qs = np.asarray(GOLDEN["queries"] * 4, np.float32)          # 16 queries → batched kernel
+    batch = asyncio.run(s.search_batch(qs, top_k=5, filters={"source": {"$in": ["file0.pdf", "file3.pdf"]}}))
+    for j in range(16):
+        single = asyncio.run(s.search(qs[j].tolist(), top_k=5, filters={"source": {"$in": ["file0.pdf", "file3.pdf"]}}))
+        assert [c.id for c, _ in batch[j]] == [c.id for c, _ in single]
+        np.testing.assert_allclose([sc for _, sc in batch[j]], [sc for _, sc in single], atol=3e-6)

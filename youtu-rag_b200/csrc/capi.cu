@@ -333,7 +333,7 @@ int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* ou
     int path = ix->path;
     if (path == 0) {
         if (k > YRB_FUSED_K_MAX) path = 3;
-        else if (nq >= 8 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
+        else if (nq >= 8 && ix->metric != YRB_METRIC_L2 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
         else path = 1;
     }
     if (path == 2 && !yrb::k2_supported(ix->dtype, ix->dim, k))

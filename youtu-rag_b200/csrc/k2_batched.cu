@@ -1,17 +1,570 @@
-// K2 placeholder while K1 is validated on hardware; replaced by the tcgen05 kernel.
-#include "k2_batched.h"
+// K2 — batched search: bf16 tcgen05 GEMM (TMA-fed, TMEM accumulators) with a fused top-k epilogue,
+// so the [queries x rows] score matrix never reaches HBM.
+//
+// Stands in for the loop of single searches the reference runs for a batch
+// (VectorRetriever.batch_retrieve, utu/rag/knowledge_retrieval/base_retriever.py:95-99, each a
+// collection.query, chroma_store.py:118-120), computed exactly.
+//
+// Shape of the work.  The GEMM is issued "transposed": MMA-M = 128 queries (A operand),
+// MMA-N = 128 corpus rows (B operand), K = 16 per instruction, both operands K-major in shared memory
+// with the 128-byte swizzle TMA produces.  TMEM lane = query, TMEM column = corpus row of the tile, so
+// an epilogue thread owns ONE query: its running threshold and candidate count live in registers and
+// there are no atomics or shared-memory lists in the epilogue.
+//   warp 0     TMA producer (corpus tile from HBM, query k-block from L2) into a 4/6-stage ring
+//   warp 1     tcgen05.mma issuer (one thread), commits release ring slots and publish accumulators
+//   warp 2     TMEM allocator
+//   warps 4..  epilogue: tcgen05.ld 32 columns, compare with the query's threshold, append survivors
+//              (64-bit keys) to the per-(CTA,query) candidate buffer in global memory (L2 resident)
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Thresholds: phase A scans one tile per CTA with no threshold and publishes each query's best
+// scores; a tiny kernel turns them into a valid lower bound of the k-th best score (the k-th largest
+// of a set of real row scores); phase B scans the rest with that bound, so only ~O(k) candidates per
+// query survive chip-wide.  A buffer that fills up is compacted in place (warp bitonic sort).  The final
+// kernel selects the sorted top-k per query from all candidate buffers.
+// Algorithmic flops 2·nq·N·D; algorithmic bytes N·ld·2 (corpus, once) + nq·ld·2.
+#include <cuda.h>
+#include <cuda_bf16.h>
 
+#include "../../include/yrb200.h"
+#include "common.cuh"
+#include "k2_batched.h"
 #include "kernels.h"
+
 namespace yrb {
-struct K2State {};
+
+namespace k2 {
+
+constexpr int BLOCK_Q = 128;   // MMA M: queries per query block
+constexpr int BLOCK_R = 128;   // MMA N: corpus rows per tile
+constexpr int BLOCK_K = 64;    // bf16 elements per k-block = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int CAP = 256;       // candidate slots per (CTA, query)
+constexpr int MAX_Q = 256;     // queries per launch (2 query blocks)
+constexpr int TILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 16 KiB
+constexpr int MAX_TOPS = 2;
+
+__host__ __device__ constexpr int stages(int qb) { return qb == 2 ? 4 : 6; }
+__host__ __device__ constexpr int stage_bytes(int qb) { return (qb + 1) * TILE_BYTES; }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+        "%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (version 1 = Blackwell):
+// start address >> 4 | LBO(1) << 16 | SBO (8 rows x 128 B = 1024 B >> 4) << 32 | version << 46 | layout(2) << 61
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_R >> 3) << 17) |
+                           ((uint32_t)(BLOCK_Q >> 4) << 24);
+
+// ---------------------------------------------------------------- warp bitonic sort of 256 keys
+// element e = i*32 + lane, descending.
+__device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 256; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int ri = stride >> 5;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if ((i & ri) == 0) {
+                        const int e = i * 32 + lane;
+                        const bool desc = (e & size) == 0;
+                        uint64_t a = v[i], b = v[i | ri];
+                        const bool sw = desc ? (b > a) : (a > b);
+                        v[i] = sw ? b : a;
+                        v[i | ri] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int e = i * 32 + lane;
+                    const bool desc = (e & size) == 0;
+                    const bool lower = (lane & stride) == 0;
+                    const uint64_t o = shfl_xor_u64(v[i], stride);
+                    const uint64_t mx = v[i] > o ? v[i] : o, mn = v[i] > o ? o : v[i];
+                    v[i] = (lower == desc) ? mx : mn;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int QB>
+__global__ void __launch_bounds__(128 + 128 * QB, 1)
+    k2_gemm_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows,
+                 int kblocks, int tile_begin, int tile_end, int nq, int k, const uint32_t* __restrict__ mask,
+                 const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
+                 float* __restrict__ tops, int m_tops) {
+    constexpr int S = stages(QB);
+    constexpr int SB = stage_bytes(QB);
+    constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2 * S + 4];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = (smem_u32(smem) + 1023u) & ~1023u;
+    auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+    auto empty_bar = [&](int s) { return smem_u32(&bars[S + s]); };
+    auto tfull_bar = [&](int b) { return smem_u32(&bars[2 * S + b]); };
+    auto tempty_bar = [&](int b) { return smem_u32(&bars[2 * S + 2 + b]); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4 * QB);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                     "r"(2 * ACC_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    // this CTA's tiles: tile_begin + blockIdx.x + i * gridDim.x
+    const int first = tile_begin + (int)blockIdx.x;
+    const int step = (int)gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = first; t < tile_end; t += step) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), SB);
+                    const uint32_t dst = smem0 + s * SB;
+#pragma unroll
+                    for (int qb = 0; qb < QB; ++qb)
+                        tma_load_2d(dst + qb * TILE_BYTES, &tmap_q, full_bar(s), kb * BLOCK_K, qb * BLOCK_Q);
+                    tma_load_2d(dst + QB * TILE_BYTES, &tmap_r, full_bar(s), kb * BLOCK_K, t * BLOCK_R);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int buf = 0;
+            uint32_t bph = 0;
+            for (int t = first; t < tile_end; t += step) {
+                mbar_wait(tempty_bar(buf), bph ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem0 + s * SB;
+                    const uint64_t bdesc = smem_desc(a0 + QB * TILE_BYTES);
+#pragma unroll
+                    for (int qb = 0; qb < QB; ++qb) {
+                        const uint64_t adesc = smem_desc(a0 + qb * TILE_BYTES);
+                        const uint32_t d = tmem_base + buf * ACC_COLS + qb * BLOCK_R;
+#pragma unroll
+                        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
+                            umma_bf16(d, adesc + 2 * k4, bdesc + 2 * k4, IDESC, (kb | k4) != 0);
+                    }
+                    umma_commit(empty_bar(s));
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                umma_commit(tfull_bar(buf));
+                if (++buf == 2) {
+                    buf = 0;
+                    bph ^= 1;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int qb = ew >> 2, quarter = warp & 3;
+        const int qi = qb * BLOCK_Q + quarter * 32 + lane;
+        const bool active = qi < nq;
+        const int64_t slot = (int64_t)blockIdx.x * MAX_Q + qi;
+        uint64_t* buf_keys = cand_keys + slot * CAP;
+        int cnt = active ? cand_cnt[slot] : 0;
+        float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
+        if (!active) thr = INFINITY;
+        float t0 = -INFINITY, t1 = -INFINITY;
+        int buf = 0;
+        uint32_t bph = 0;
+        for (int t = first; t < tile_end; t += step) {
+            mbar_wait(tfull_bar(buf), bph);
+            tc_fence_after();
+            const int64_t row0 = (int64_t)t * BLOCK_R;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_R / 32; ++c) {
+                // make room for up to 32 appends: compact any lane's buffer that is nearly full
+                unsigned need = __ballot_sync(YRB_FULL, cnt > CAP - 32);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int n = __shfl_sync(YRB_FULL, cnt, L);
+                    const uint64_t base = shfl_u64((uint64_t)buf_keys, L);
+                    uint64_t* bp = reinterpret_cast<uint64_t*>(base);
+                    uint64_t v[8];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (i * 32 + lane < n) ? bp[i * 32 + lane] : 0ull;
+                    warp_sort256_desc(v, lane);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i * 32 + lane < k) bp[i * 32 + lane] = v[i];
+                    uint64_t kth = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint64_t x = shfl_u64(v[i], (k - 1) & 31);
+                        if (((k - 1) >> 5) == i) kth = x;
+                    }
+                    __syncwarp();
+                    if (lane == L) {
+                        cnt = n < k ? n : k;
+                        if (n >= k) thr = key_score(kth);
+                    }
+                }
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + qb * BLOCK_R + c * 32, v);
+                const int64_t r0 = row0 + c * 32;
+                uint32_t mw = 0u;
+                if (r0 < n_rows) {
+                    mw = mask ? mask[r0 >> 5] : 0xffffffffu;
+                    if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v[j]);
+                    if (((mw >> j) & 1u) && s > thr) {
+                        buf_keys[cnt++] = make_key(s, (uint32_t)(r0 + j));
+                        if (s > t1) {
+                            if (s > t0) {
+                                t1 = t0;
+                                t0 = s;
+                            } else {
+                                t1 = s;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (++buf == 2) {
+                buf = 0;
+                bph ^= 1;
+            }
+        }
+        if (active) {
+            cand_cnt[slot] = cnt;
+            if (tops) {
+                tops[((int64_t)blockIdx.x * MAX_TOPS + 0) * MAX_Q + qi] = t0;
+                if (m_tops > 1) tops[((int64_t)blockIdx.x * MAX_TOPS + 1) * MAX_Q + qi] = t1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS));
+    }
+}
+
+// ---------------------------------------------------------------- thresholds from phase A
+// thr0[q] = k-th largest of the (n_cta * m) published best scores: every one is the score of a distinct
+// real row, so at least k rows score >= thr0[q] and thr0[q] <= the true k-th best.  Fewer than k → -inf.
+__global__ void __launch_bounds__(256) k2_threshold_kernel(const float* __restrict__ tops, int n_cta, int m, int k,
+                                                           float* __restrict__ thr0) {
+    __shared__ float sv[512];
+    const int q = blockIdx.x;
+    const int n = n_cta * m;
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        float v = -INFINITY;
+        if (i < n) v = tops[((int64_t)(i / m) * MAX_TOPS + (i % m)) * MAX_Q + q];
+        sv[i] = v;
+    }
+    block_bitonic_desc(sv, 512, [](float a, float b) { return a > b; });
+    if (threadIdx.x == 0) {
+        float t = (n >= k) ? sv[k - 1] : -INFINITY;
+        // one ulp below the k-th published score: rows tying with it still pass the strict `s > thr`
+        thr0[q] = nextafterf(t, -INFINITY);
+    }
+}
+
+// ---------------------------------------------------------------- final selection
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_CAP = 8192;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+    k2_select_kernel(const uint64_t* __restrict__ cand_keys, const int* __restrict__ cand_cnt, int n_slots, int k,
+                     uint64_t* __restrict__ out_keys) {
+    extern __shared__ __align__(16) unsigned char sraw[];
+    uint64_t* sk = reinterpret_cast<uint64_t*>(sraw);
+    __shared__ int s_cnt[256];
+    __shared__ int s_off[257];
+    __shared__ int s_group_end, s_total;
+    const int q = blockIdx.x;
+    for (int b = threadIdx.x; b < n_slots; b += blockDim.x) {
+        int c = cand_cnt[(int64_t)b * MAX_Q + q];
+        s_cnt[b] = c > CAP ? CAP : c;
+    }
+    __syncthreads();
+    int have = 0;   // entries carried over (best so far), stored at sk[0..have)
+    int b0 = 0;
+    while (b0 < n_slots) {
+        if (threadIdx.x == 0) {
+            int tot = have, b = b0;
+            s_off[b0] = have;
+            while (b < n_slots && tot + s_cnt[b] <= SEL_CAP) {
+                tot += s_cnt[b];
+                ++b;
+                s_off[b] = tot;
+            }
+            s_group_end = b;
+            s_total = tot;
+        }
+        __syncthreads();
+        const int b1 = s_group_end, total = s_total;
+        for (int b = b0 + (threadIdx.x >> 5); b < b1; b += (blockDim.x >> 5)) {
+            const uint64_t* src = cand_keys + ((int64_t)b * MAX_Q + q) * CAP;
+            for (int i = threadIdx.x & 31; i < s_cnt[b]; i += 32) sk[s_off[b] + i] = src[i];
+        }
+        const int npow = next_pow2(total > 1 ? total : 2);
+        for (int i = total + threadIdx.x; i < npow; i += blockDim.x) sk[i] = 0ull;
+        block_bitonic_desc(sk, npow, BetterU64());
+        have = total < k ? total : k;
+        b0 = b1;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out_keys[(int64_t)q * k + i] = (i < have) ? sk[i] : 0ull;
+}
+
+}  // namespace k2
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct K2State {
+    EncodeTiledFn encode = nullptr;
+    int slots = 0;
+    uint64_t* cand_keys = nullptr;
+    int* cand_cnt = nullptr;
+    float* tops = nullptr;
+    float* thr0 = nullptr;
+    bool attrs_set = false;
+};
+
 K2State* k2_create() { return new K2State(); }
-void k2_destroy(K2State* s) { delete s; }
+void k2_destroy(K2State* s) {
+    if (!s) return;
+    if (s->cand_keys) cudaFree(s->cand_keys);
+    if (s->cand_cnt) cudaFree(s->cand_cnt);
+    if (s->tops) cudaFree(s->tops);
+    if (s->thr0) cudaFree(s->thr0);
+    delete s;
+}
 void k2_invalidate(K2State*) {}
 int k2_parts(int sm_count) { return sm_count; }
-bool k2_supported(int, int, int) { return false; }
-int k2_search(K2State*, const void*, int64_t, int64_t, int, int, const void*, int, int, const uint32_t*, int,
-              const float*, const float*, uint64_t*, uint64_t*, int, cudaStream_t, int*, std::string& err) {
-    err = "K2 not built";
-    return -4;
+bool k2_supported(int dtype, int dim, int k) { return dtype == 0 && dim >= 1 && k >= 1 && k <= YRB_FUSED_K_MAX; }
+
+static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows, int ld, std::string& err) {
+    cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)k2::BLOCK_K, (cuuint32_t)k2::BLOCK_R};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = s->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
 }
+
+#define K2CK(call)                                                                     \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            err = std::string(#call) + ": " + cudaGetErrorString(e_);                  \
+            return YRB_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+template <int QB>
+static cudaError_t launch_gemm(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks,
+                               int tile_begin, int tile_end, int nq, int k, const uint32_t* mask, const float* thr,
+                               uint64_t* ck, int* cc, float* tops, int m_tops, cudaStream_t st) {
+    const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
+    auto kern = k2::k2_gemm_topk<QB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 128 + 128 * QB, smem, st>>>(mq, mr, n_rows, kblocks, tile_begin, tile_end, nq, k, mask, thr, ck, cc,
+                                             tops, m_tops);
+    return cudaGetLastError();
+}
+
+int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
+              int k, const uint32_t* mask, int metric, const float* q_sqnorm, const float* row_sqnorm,
+              uint64_t* out_keys, uint64_t* scratch, int sm_count, cudaStream_t st, int* launches, std::string& err) {
+    (void)capacity; (void)dim; (void)q_sqnorm; (void)row_sqnorm; (void)scratch;
+    if (metric == YRB_METRIC_L2) {
+        err = "K2 handles cosine / dot; euclidean goes through K1";
+        return YRB_ERR_UNSUPPORTED;
+    }
+    if (!s->encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        K2CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            err = "cuTensorMapEncodeTiled not available from the driver";
+            return YRB_ERR_UNSUPPORTED;
+        }
+        s->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    if (s->slots < sm_count) {
+        if (s->cand_keys) cudaFree(s->cand_keys);
+        if (s->cand_cnt) cudaFree(s->cand_cnt);
+        if (s->tops) cudaFree(s->tops);
+        if (s->thr0) cudaFree(s->thr0);
+        s->cand_keys = nullptr; s->cand_cnt = nullptr; s->tops = nullptr; s->thr0 = nullptr;
+        K2CK(cudaMalloc(&s->cand_keys, (size_t)sm_count * k2::MAX_Q * k2::CAP * 8));
+        K2CK(cudaMalloc(&s->cand_cnt, (size_t)sm_count * k2::MAX_Q * 4));
+        K2CK(cudaMalloc(&s->tops, (size_t)sm_count * k2::MAX_TOPS * k2::MAX_Q * 4));
+        K2CK(cudaMalloc(&s->thr0, (size_t)k2::MAX_Q * 4));
+        s->slots = sm_count;
+    }
+    const int kblocks = ld / k2::BLOCK_K;
+    const int tiles = (int)((n_rows + k2::BLOCK_R - 1) / k2::BLOCK_R);
+    CUtensorMap mr;
+    if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, err)) return YRB_ERR_CUDA;
+    const size_t sel_smem = (size_t)k2::SEL_CAP * 8;
+    K2CK(cudaFuncSetAttribute(k2::k2_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+
+    for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
+        const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
+        const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
+        CUtensorMap mq;
+        if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld, err))
+            return YRB_ERR_CUDA;
+        K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)sm_count * k2::MAX_Q * 4, st));
+        // phase A: one tile per CTA, no threshold; publishes the best scores of each query
+        const int gridA = tiles < sm_count ? tiles : sm_count;
+        const int m_tops = (2 * k + gridA - 1) / gridA <= 1 ? 1 : k2::MAX_TOPS;
+        const bool two_phase = tiles > gridA && (int64_t)gridA * m_tops >= k;
+        if (QB == 2)
+            K2CK(launch_gemm<2>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys, s->cand_cnt,
+                                two_phase ? s->tops : nullptr, m_tops, st));
+        else
+            K2CK(launch_gemm<1>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys, s->cand_cnt,
+                                two_phase ? s->tops : nullptr, m_tops, st));
+        ++*launches;
+        int n_slots = gridA;
+        if (tiles > gridA) {
+            const float* thr = nullptr;
+            if (two_phase) {
+                k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
+                K2CK(cudaGetLastError());
+                ++*launches;
+                thr = s->thr0;
+            }
+            const int gridB = (tiles - gridA) < sm_count ? (tiles - gridA) : sm_count;
+            if (QB == 2)
+                K2CK(launch_gemm<2>(gridB, mq, mr, n_rows, kblocks, gridA, tiles, nqc, k, mask, thr, s->cand_keys,
+                                    s->cand_cnt, nullptr, 0, st));
+            else
+                K2CK(launch_gemm<1>(gridB, mq, mr, n_rows, kblocks, gridA, tiles, nqc, k, mask, thr, s->cand_keys,
+                                    s->cand_cnt, nullptr, 0, st));
+            ++*launches;
+            n_slots = gridA > gridB ? gridA : gridB;
+        }
+        k2::k2_select_kernel<<<nqc, k2::SEL_THREADS, sel_smem, st>>>(s->cand_keys, s->cand_cnt, n_slots, k,
+                                                                      out_keys + (size_t)c0 * k);
+        K2CK(cudaGetLastError());
+        ++*launches;
+    }
+    return YRB_OK;
+}
+
 }  // namespace yrb
