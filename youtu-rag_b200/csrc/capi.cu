@@ -310,6 +310,28 @@ int prof_flush(yrb_index* ix) {
     return YRB_OK;
 }
 
+// reserves the next (start, stop) event pair for code that records them itself
+int prof_pair(yrb_index* ix, cudaEvent_t* a, cudaEvent_t* b) {
+    *a = *b = nullptr;
+    if (!ix->prof) return YRB_OK;
+    if (ix->prof_used + 2 > ix->prof_ev.size()) {
+        if (ix->prof_ev.size() >= 8192) {
+            int rc = prof_flush(ix);
+            if (rc) return rc;
+        } else {
+            cudaEvent_t x, y;
+            CK(cudaEventCreate(&x));
+            CK(cudaEventCreate(&y));
+            ix->prof_ev.push_back(x);
+            ix->prof_ev.push_back(y);
+        }
+    }
+    *a = ix->prof_ev[ix->prof_used];
+    *b = ix->prof_ev[ix->prof_used + 1];
+    ix->prof_used += 2;
+    return YRB_OK;
+}
+
 int prof_mark(yrb_index* ix, cudaStream_t st) {
     if (!ix->prof) return YRB_OK;
     if (ix->prof_used == ix->prof_ev.size()) {
@@ -343,13 +365,13 @@ int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* ou
     const size_t es = yrb::elem_size(ix->dtype);
     if (path == 2) {
         int launches = 0;
-        int rc = prof_mark(ix, st);
+        cudaEvent_t ea, eb;
+        int rc = prof_pair(ix, &ea, &eb);
         if (rc) return rc;
         rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
                                 ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ix->d_mscratch, ix->sm_count, st,
-                                &launches, g_err);
+                                &launches, g_err, ea, eb);
         ix->launches += launches;
-        if (!rc) rc = prof_mark(ix, st);
         return rc;
     }
     if (path == 1) {
@@ -362,7 +384,7 @@ int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* ou
                               reinterpret_cast<const char*>(ix->d_q) + (size_t)j * ix->ld * es, ix->d_qsq + j,
                               ix->d_sqnorm, ix->metric, mask, k, pk, ix->sm_count, st));
             if ((rc = prof_mark(ix, st))) return rc;
-            CK(yrb::launch_merge_keys(pk, parts, 1, k, out_keys + (size_t)j * k, ix->d_mscratch, st));
+            CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, parts, k, k, nullptr, 1, k, out_keys + (size_t)j * k, st));
             ix->launches += 2;
         }
         return YRB_OK;

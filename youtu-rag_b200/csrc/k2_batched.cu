@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
         float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
         if (!active) thr = INFINITY;
         float t0 = -INFINITY, t1 = -INFINITY;
+        const bool sample_only = tops != nullptr;  // phase A: publish the best scores, append nothing
         int buf = 0;
         uint32_t bph = 0;
         for (int t = first; t < tile_end; t += step) {
@@ -308,12 +309,11 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     mw = mask ? mask[r0 >> 5] : 0xffffffffu;
                     if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
                 }
+                if (sample_only) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float s = __uint_as_float(v[j]);
-                    if (((mw >> j) & 1u) && s > thr) {
-                        buf_keys[cnt++] = make_key(s, (uint32_t)(r0 + j));
-                        if (s > t1) {
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (((mw >> j) & 1u) && s > t1) {
                             if (s > t0) {
                                 t1 = t0;
                                 t0 = s;
@@ -321,6 +321,12 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                                 t1 = s;
                             }
                         }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (((mw >> j) & 1u) && s > thr) buf_keys[cnt++] = make_key(s, (uint32_t)(r0 + j));
                     }
                 }
             }
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             }
         }
         if (active) {
-            cand_cnt[slot] = cnt;
+            if (!sample_only) cand_cnt[slot] = cnt;
             if (tops) {
                 tops[((int64_t)blockIdx.x * MAX_TOPS + 0) * MAX_Q + qi] = t0;
                 if (m_tops > 1) tops[((int64_t)blockIdx.x * MAX_TOPS + 1) * MAX_Q + qi] = t1;
@@ -368,54 +374,6 @@ __global__ void __launch_bounds__(256) k2_threshold_kernel(const float* __restri
         // one ulp below the k-th published score: rows tying with it still pass the strict `s > thr`
         thr0[q] = nextafterf(t, -INFINITY);
     }
-}
-
-// ---------------------------------------------------------------- final selection
-constexpr int SEL_THREADS = 1024;
-constexpr int SEL_CAP = 8192;
-
-__global__ void __launch_bounds__(SEL_THREADS)
-    k2_select_kernel(const uint64_t* __restrict__ cand_keys, const int* __restrict__ cand_cnt, int n_slots, int k,
-                     uint64_t* __restrict__ out_keys) {
-    extern __shared__ __align__(16) unsigned char sraw[];
-    uint64_t* sk = reinterpret_cast<uint64_t*>(sraw);
-    __shared__ int s_cnt[256];
-    __shared__ int s_off[257];
-    __shared__ int s_group_end, s_total;
-    const int q = blockIdx.x;
-    for (int b = threadIdx.x; b < n_slots; b += blockDim.x) {
-        int c = cand_cnt[(int64_t)b * MAX_Q + q];
-        s_cnt[b] = c > CAP ? CAP : c;
-    }
-    __syncthreads();
-    int have = 0;   // entries carried over (best so far), stored at sk[0..have)
-    int b0 = 0;
-    while (b0 < n_slots) {
-        if (threadIdx.x == 0) {
-            int tot = have, b = b0;
-            s_off[b0] = have;
-            while (b < n_slots && tot + s_cnt[b] <= SEL_CAP) {
-                tot += s_cnt[b];
-                ++b;
-                s_off[b] = tot;
-            }
-            s_group_end = b;
-            s_total = tot;
-        }
-        __syncthreads();
-        const int b1 = s_group_end, total = s_total;
-        for (int b = b0 + (threadIdx.x >> 5); b < b1; b += (blockDim.x >> 5)) {
-            const uint64_t* src = cand_keys + ((int64_t)b * MAX_Q + q) * CAP;
-            for (int i = threadIdx.x & 31; i < s_cnt[b]; i += 32) sk[s_off[b] + i] = src[i];
-        }
-        const int npow = next_pow2(total > 1 ? total : 2);
-        for (int i = total + threadIdx.x; i < npow; i += blockDim.x) sk[i] = 0ull;
-        block_bitonic_desc(sk, npow, BetterU64());
-        have = total < k ? total : k;
-        b0 = b1;
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < k; i += blockDim.x) out_keys[(int64_t)q * k + i] = (i < have) ? sk[i] : 0ull;
 }
 
 }  // namespace k2
@@ -487,7 +445,8 @@ static cudaError_t launch_gemm(int grid, const CUtensorMap& mq, const CUtensorMa
 
 int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
               int k, const uint32_t* mask, int metric, const float* q_sqnorm, const float* row_sqnorm,
-              uint64_t* out_keys, uint64_t* scratch, int sm_count, cudaStream_t st, int* launches, std::string& err) {
+              uint64_t* out_keys, uint64_t* scratch, int sm_count, cudaStream_t st, int* launches, std::string& err,
+              cudaEvent_t ev_start, cudaEvent_t ev_stop) {
     (void)capacity; (void)dim; (void)q_sqnorm; (void)row_sqnorm; (void)scratch;
     if (metric == YRB_METRIC_L2) {
         err = "K2 handles cosine / dot; euclidean goes through K1";
@@ -519,8 +478,6 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
     const int tiles = (int)((n_rows + k2::BLOCK_R - 1) / k2::BLOCK_R);
     CUtensorMap mr;
     if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, err)) return YRB_ERR_CUDA;
-    const size_t sel_smem = (size_t)k2::SEL_CAP * 8;
-    K2CK(cudaFuncSetAttribute(k2::k2_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
 
     for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
         const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
@@ -529,40 +486,37 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld, err))
             return YRB_ERR_CUDA;
         K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)sm_count * k2::MAX_Q * 4, st));
-        // phase A: one tile per CTA, no threshold; publishes the best scores of each query
+        // phase A (sampling): the first tile of each CTA is scored only to publish each query's best
+        // scores; thr0 = k-th largest of them is a valid lower bound of the k-th best overall.
         const int gridA = tiles < sm_count ? tiles : sm_count;
         const int m_tops = (2 * k + gridA - 1) / gridA <= 1 ? 1 : k2::MAX_TOPS;
-        const bool two_phase = tiles > gridA && (int64_t)gridA * m_tops >= k;
-        if (QB == 2)
-            K2CK(launch_gemm<2>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys, s->cand_cnt,
-                                two_phase ? s->tops : nullptr, m_tops, st));
-        else
-            K2CK(launch_gemm<1>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys, s->cand_cnt,
-                                two_phase ? s->tops : nullptr, m_tops, st));
-        ++*launches;
-        int n_slots = gridA;
-        if (tiles > gridA) {
-            const float* thr = nullptr;
-            if (two_phase) {
-                k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
-                K2CK(cudaGetLastError());
-                ++*launches;
-                thr = s->thr0;
-            }
-            const int gridB = (tiles - gridA) < sm_count ? (tiles - gridA) : sm_count;
+        const bool sampled = tiles > 2 * gridA && (int64_t)gridA * m_tops >= k;
+        const float* thr = nullptr;
+        if (sampled) {
             if (QB == 2)
-                K2CK(launch_gemm<2>(gridB, mq, mr, n_rows, kblocks, gridA, tiles, nqc, k, mask, thr, s->cand_keys,
-                                    s->cand_cnt, nullptr, 0, st));
+                K2CK(launch_gemm<2>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys,
+                                    s->cand_cnt, s->tops, m_tops, st));
             else
-                K2CK(launch_gemm<1>(gridB, mq, mr, n_rows, kblocks, gridA, tiles, nqc, k, mask, thr, s->cand_keys,
-                                    s->cand_cnt, nullptr, 0, st));
-            ++*launches;
-            n_slots = gridA > gridB ? gridA : gridB;
+                K2CK(launch_gemm<1>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys,
+                                    s->cand_cnt, s->tops, m_tops, st));
+            k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
+            K2CK(cudaGetLastError());
+            *launches += 2;
+            thr = s->thr0;
         }
-        k2::k2_select_kernel<<<nqc, k2::SEL_THREADS, sel_smem, st>>>(s->cand_keys, s->cand_cnt, n_slots, k,
-                                                                      out_keys + (size_t)c0 * k);
-        K2CK(cudaGetLastError());
-        ++*launches;
+        // phase B: every tile, with the bound
+        const int gridB = tiles < sm_count ? tiles : sm_count;
+        if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
+        if (QB == 2)
+            K2CK(launch_gemm<2>(gridB, mq, mr, n_rows, kblocks, 0, tiles, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
+                                nullptr, 0, st));
+        else
+            K2CK(launch_gemm<1>(gridB, mq, mr, n_rows, kblocks, 0, tiles, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
+                                nullptr, 0, st));
+        if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
+        K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,
+                                    k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st));
+        *launches += 2;
     }
     return YRB_OK;
 }

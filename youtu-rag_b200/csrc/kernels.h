@@ -35,6 +35,13 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
 // scratch must hold parts*nq*k keys when parts*k > 4096 (multi-pass).
 cudaError_t launch_merge_keys(const uint64_t* in, int parts, int nq, int k, uint64_t* out,
                               uint64_t* scratch, cudaStream_t st);
+// sorted top-k of unsorted candidates gathered from n_seg segments per query (see k3_select.cu):
+// key pointer of (seg, q) = base + seg*seg_stride + q*q_stride; its length = counts[seg*cnt_seg_stride +
+// q*cnt_q_stride] (or fixed_cnt), clamped to seg_cap; zero keys are skipped; thr (optional) keeps
+// only keys whose score > thr[q].  k <= 256.
+cudaError_t launch_select_segments(const uint64_t* base, int64_t seg_stride, int64_t q_stride, const int* counts,
+                                   int64_t cnt_seg_stride, int64_t cnt_q_stride, int n_seg, int fixed_cnt, int seg_cap,
+                                   const float* thr, int nq, int k, uint64_t* out, cudaStream_t st);
 // keys [nq][k] → ids / scores / counts
 cudaError_t launch_decode(const uint64_t* keys, int nq, int k, int64_t* ids, float* scores,
                           int32_t* counts, cudaStream_t st);
