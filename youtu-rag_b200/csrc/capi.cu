@@ -70,9 +70,12 @@ struct yrb_index {
     uint64_t* d_parts = nullptr;
     uint64_t* d_keys = nullptr;
     uint64_t* d_mscratch = nullptr;
-    int64_t* d_ids = nullptr;
+    unsigned char* d_result = nullptr;  // [ids nq*k i64 | scores nq*k f32 | counts nq i32], one D2H
+    size_t result_bytes = 0;
+    int64_t* d_ids = nullptr;           // views into d_result for the current (nq, k)
     float* d_scores = nullptr;
     int32_t* d_counts = nullptr;
+    unsigned int* d_ticket = nullptr;   // K1's last-CTA-done counter
     float* d_rowscores = nullptr;  // K6, capacity floats
     void* d_select = nullptr;
     size_t select_bytes = 0;
@@ -81,9 +84,7 @@ struct yrb_index {
     unsigned long long* d_pass = nullptr;
     // pinned staging
     float* h_q = nullptr;
-    int64_t* h_ids = nullptr;
-    float* h_scores = nullptr;
-    int32_t* h_counts = nullptr;
+    unsigned char* h_result = nullptr;
     void* h_stage = nullptr;
     size_t stage_bytes = 0;
     yrb::K2State* k2 = nullptr;
@@ -175,13 +176,12 @@ void free_scratch(yrb_index* ix) {
     FREE_DEV(ix->d_parts);
     FREE_DEV(ix->d_keys);
     FREE_DEV(ix->d_mscratch);
-    FREE_DEV(ix->d_ids);
-    FREE_DEV(ix->d_scores);
-    FREE_DEV(ix->d_counts);
+    FREE_DEV(ix->d_result);
+    ix->d_ids = nullptr;
+    ix->d_scores = nullptr;
+    ix->d_counts = nullptr;
     FREE_HOST(ix->h_q);
-    FREE_HOST(ix->h_ids);
-    FREE_HOST(ix->h_scores);
-    FREE_HOST(ix->h_counts);
+    FREE_HOST(ix->h_result);
     ix->nq_cap = ix->k_cap = 0;
 }
 
@@ -198,16 +198,21 @@ int ensure_scratch(yrb_index* ix, int nq, int k) {
     CK(cudaMalloc(&ix->d_parts, (size_t)parts * nqc * kc * 8));
     CK(cudaMalloc(&ix->d_keys, (size_t)nqc * kc * 8));
     CK(cudaMalloc(&ix->d_mscratch, (size_t)parts * nqc * kc * 8));
-    CK(cudaMalloc(&ix->d_ids, (size_t)nqc * kc * 8));
-    CK(cudaMalloc(&ix->d_scores, (size_t)nqc * kc * 4));
-    CK(cudaMalloc(&ix->d_counts, (size_t)nqc * 4));
+    ix->result_bytes = (size_t)nqc * kc * 12 + (size_t)nqc * 4;
+    CK(cudaMalloc(&ix->d_result, ix->result_bytes));
     CK(cudaMallocHost(&ix->h_q, (size_t)nqc * ix->dim * 4));
-    CK(cudaMallocHost(&ix->h_ids, (size_t)nqc * kc * 8));
-    CK(cudaMallocHost(&ix->h_scores, (size_t)nqc * kc * 4));
-    CK(cudaMallocHost(&ix->h_counts, (size_t)nqc * 4));
+    CK(cudaMallocHost(&ix->h_result, ix->result_bytes));
     ix->nq_cap = nqc;
     ix->k_cap = kc;
     return YRB_OK;
+}
+
+// carve d_result for this call's (nq, k): ids | scores | counts, contiguous → one D2H copy
+size_t result_views(yrb_index* ix, int nq, int k) {
+    ix->d_ids = reinterpret_cast<int64_t*>(ix->d_result);
+    ix->d_scores = reinterpret_cast<float*>(ix->d_result + (size_t)nq * k * 8);
+    ix->d_counts = reinterpret_cast<int32_t*>(ix->d_result + (size_t)nq * k * 12);
+    return (size_t)nq * k * 12 + (size_t)nq * 4;
 }
 
 // upload the host mirror of a bitmask range [w0, w1)
@@ -350,27 +355,32 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
     return YRB_OK;
 }
 
-// queries already prepared in ix->d_q / ix->d_qsq; writes nq*k keys
-int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* out_keys, cudaStream_t st) {
+// raw fp32 queries [nq, dim] on the device → nq*k keys (and, when `decode`, ix->d_ids/d_scores/d_counts).
+// K1 prepares the query in its own prologue; K2 needs the prepared bf16 matrix (K5 launch).
+int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, uint64_t* out_keys, bool decode,
+                cudaStream_t st) {
     int path = ix->path;
     if (path == 0) {
         if (k > YRB_FUSED_K_MAX) path = 3;
         else if (nq >= 8 && ix->metric != YRB_METRIC_L2 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
         else path = 1;
     }
-    if (path == 2 && !yrb::k2_supported(ix->dtype, ix->dim, k))
-        return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage and k <= %d", YRB_FUSED_K_MAX);
+    if (path == 2 && (ix->metric == YRB_METRIC_L2 || !yrb::k2_supported(ix->dtype, ix->dim, k)))
+        return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage, cosine/dot and k <= %d", YRB_FUSED_K_MAX);
     if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
         return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
-    const size_t es = yrb::elem_size(ix->dtype);
+    int64_t* ids = decode ? ix->d_ids : nullptr;
+    float* scores = decode ? ix->d_scores : nullptr;
+    int32_t* counts = decode ? ix->d_counts : nullptr;
     if (path == 2) {
-        int launches = 0;
+        CK(yrb::launch_ingest(dev_q, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
+        int launches = 1;
         cudaEvent_t ea, eb;
         int rc = prof_pair(ix, &ea, &eb);
         if (rc) return rc;
         rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
-                                ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ix->d_mscratch, ix->sm_count, st,
-                                &launches, g_err, ea, eb);
+                            ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, ix->sm_count, st,
+                            &launches, g_err, ea, eb);
         ix->launches += launches;
         return rc;
     }
@@ -378,14 +388,20 @@ int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* ou
         const int parts = yrb::k1_parts(ix->sm_count);
         for (int j = 0; j < nq; ++j) {
             uint64_t* pk = ix->d_parts + (size_t)j * parts * k;
+            yrb::K1Out o{out_keys + (size_t)j * k, ids ? ids + (size_t)j * k : nullptr,
+                         scores ? scores + (size_t)j * k : nullptr, counts ? counts + j : nullptr};
+            bool fused = false;
             int rc = prof_mark(ix, st);
             if (rc) return rc;
-            CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld,
-                              reinterpret_cast<const char*>(ix->d_q) + (size_t)j * ix->ld * es, ix->d_qsq + j,
-                              ix->d_sqnorm, ix->metric, mask, k, pk, ix->sm_count, st));
+            CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
+                              ix->metric, mask, k, pk, ix->d_ticket, o, &fused, ix->sm_count, st));
             if ((rc = prof_mark(ix, st))) return rc;
-            CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, parts, k, k, nullptr, 1, k, out_keys + (size_t)j * k, st));
-            ix->launches += 2;
+            ix->launches++;
+            if (!fused) {
+                CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, parts, k, k, nullptr, 1, k, o.final_keys, st, o.ids,
+                                               o.scores, o.count));
+                ix->launches++;
+            }
         }
         return YRB_OK;
     }
@@ -398,11 +414,14 @@ int scan_select(yrb_index* ix, int nq, int k, const uint32_t* mask, uint64_t* ou
         ix->select_bytes = need;
     }
     for (int j = 0; j < nq; ++j) {
-        CK(yrb::launch_scores(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld,
-                              reinterpret_cast<const char*>(ix->d_q) + (size_t)j * ix->ld * es, ix->d_qsq + j,
-                              ix->d_sqnorm, ix->metric, mask, ix->d_rowscores, ix->sm_count, st));
+        CK(yrb::launch_scores(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
+                              ix->metric, mask, ix->d_rowscores, ix->sm_count, st));
         CK(yrb::launch_select(ix->d_rowscores, ix->rows, k, out_keys + (size_t)j * k, ix->d_select, ix->sm_count, st));
         ix->launches += 2;
+    }
+    if (decode) {
+        CK(yrb::launch_decode(out_keys, nq, k, ids, scores, counts, st));
+        ix->launches++;
     }
     return YRB_OK;
 }
@@ -484,6 +503,8 @@ int yrb_index_create(yrb_index** out, int device, int dim, int metric, int stora
     CKB(cudaMalloc(&ix->d_prog, sizeof(yrb::WhereProgDev)));
     CKB(cudaMallocHost(&ix->h_prog, sizeof(yrb::WhereProgDev)));
     CKB(cudaMalloc(&ix->d_pass, 8));
+    CKB(cudaMalloc(&ix->d_ticket, 4));
+    CKB(cudaMemset(ix->d_ticket, 0, 4));
 #undef CKB
     ix->k2 = yrb::k2_create();
     rc = ensure_capacity(ix, std::max<int64_t>(reserve_rows, 1));
@@ -505,6 +526,7 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_DEV(ix->d_select);
     FREE_DEV(ix->d_prog);
     FREE_DEV(ix->d_pass);
+    FREE_DEV(ix->d_ticket);
     FREE_HOST(ix->h_prog);
     FREE_HOST(ix->h_stage);
     for (auto& kv : ix->cols) {
@@ -751,8 +773,7 @@ int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const y
     cudaStream_t st = ix->stream;
     memcpy(ix->h_q, queries, (size_t)nq * ix->dim * 4);
     CK(cudaMemcpyAsync(ix->d_qf32, ix->h_q, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, st));
-    CK(yrb::launch_ingest(ix->d_qf32, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
-    ix->launches++;
+    const size_t res_bytes = result_views(ix, nq, ke);
     const uint32_t* dev_extra = nullptr;
     uint32_t* d_user = nullptr;
     if (mask) {
@@ -774,13 +795,9 @@ int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const y
     }
     const uint32_t* m = nullptr;
     rc = resolve_mask(ix, w, dev_extra, &m, st, false);
-    if (!rc) rc = scan_select(ix, nq, ke, m, ix->d_keys, st);
+    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, ix->d_keys, true, st);
     if (!rc) {
-        cudaError_t e = yrb::launch_decode(ix->d_keys, nq, ke, ix->d_ids, ix->d_scores, ix->d_counts, st);
-        ix->launches++;
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->h_ids, ix->d_ids, (size_t)nq * ke * 8, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->h_scores, ix->d_scores, (size_t)nq * ke * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ix->h_counts, ix->d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail(YRB_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
     } else {
@@ -788,13 +805,16 @@ int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const y
     }
     if (d_user) cudaFree(d_user);
     if (rc) return rc;
+    const int64_t* h_ids = reinterpret_cast<const int64_t*>(ix->h_result);
+    const float* h_scores = reinterpret_cast<const float*>(ix->h_result + (size_t)nq * ke * 8);
+    const int32_t* h_counts = reinterpret_cast<const int32_t*>(ix->h_result + (size_t)nq * ke * 12);
     for (int q = 0; q < nq; ++q) {
         for (int j = 0; j < k; ++j) {
             const bool ok = j < ke;
-            out_ids[(int64_t)q * k + j] = ok ? ix->h_ids[(int64_t)q * ke + j] : -1;
-            out_scores[(int64_t)q * k + j] = ok ? ix->h_scores[(int64_t)q * ke + j] : -INFINITY;
+            out_ids[(int64_t)q * k + j] = ok ? h_ids[(int64_t)q * ke + j] : -1;
+            out_scores[(int64_t)q * k + j] = ok ? h_scores[(int64_t)q * ke + j] : -INFINITY;
         }
-        if (out_counts) out_counts[q] = ix->h_counts[q];
+        if (out_counts) out_counts[q] = h_counts[q];
     }
     return YRB_OK;
 }
@@ -814,11 +834,9 @@ int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int
     }
     if (k > ix->rows) return fail(YRB_ERR_INVALID, "k=%d exceeds rows=%lld (device variant does not clamp)", k, (long long)ix->rows);
     if ((rc = ensure_scratch(ix, nq, k))) return rc;
-    CK(yrb::launch_ingest(dev_queries, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
-    ix->launches++;
     const uint32_t* m = nullptr;
     if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
-    return scan_select(ix, nq, k, m, dev_out_keys, st);
+    return scan_select(ix, dev_queries, nq, k, m, dev_out_keys, false, st);
 }
 
 int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int nq, int k, const int64_t* dev_row_base,

@@ -11,8 +11,11 @@
 // only touches it when a score beats the current k-th key.  Rows failing the bitmask are never
 // loaded.  Per-CTA lists are merged with a block bitonic sort; K3 merges the CTAs.
 // Algorithmic bytes per search: sel·N·ld·esize + N/8 (mask) + ld·esize (query) + parts·k·8.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "select.cuh"
 
 namespace yrb {
 
@@ -43,25 +46,50 @@ __device__ __forceinline__ float dot_chunk(uint4 v, float4 qa, float4 qb, float 
     return acc;
 }
 
-// query (storage dtype, ld16 uint4) → shared fp32, laid out [chunk][half][lane] float4 so that a
-// warp's LDS.128 is conflict-free.
+// Query preparation fused into the scan's prologue (same arithmetic as K5, csrc/k5_ingest.cu, so K1 and
+// K2 see bit-identical queries): every warp forms the fp64 sum of squares in K5's lane-strided order,
+// then the CTA writes the normalised, storage-rounded query to shared memory as fp32, laid out
+// [chunk][half][lane] float4 so that a warp's LDS.128 is conflict-free.  Returns ||stored q||^2 (fp32,
+// K5's order) when `want_sq`.
 template <bool F32>
-__device__ __forceinline__ void stage_query(const uint4* __restrict__ qv, int ld16, int nch, float4* sq) {
+__device__ __forceinline__ float prepare_query(const float* __restrict__ q_raw, int dim, int ld, int nch, int normalize,
+                                               bool want_sq, float4* sq) {
     constexpr int H = F32 ? 1 : 2;
+    constexpr int EPL = F32 ? 4 : 8;
+    const int lane = threadIdx.x & 31;
+    double ss = 0.0;
+    if (normalize) {
+        for (int i = lane; i < dim; i += 32) {
+            const double v = (double)q_raw[i];
+            ss += v * v;
+        }
+        ss = warp_sum(ss);
+    }
+    const bool scale = normalize && ss > 0.0;
+    const double nrm = scale ? sqrt(ss) : 1.0;
+    auto stored = [&](int e) -> float {
+        float y = 0.f;
+        if (e < dim) y = scale ? (float)((double)q_raw[e] / nrm) : q_raw[e];
+        return F32 ? y : __bfloat162float(__float2bfloat16_rn(y));
+    };
+    float sqn = 0.f;
+    if (want_sq) {
+        for (int i = lane; i < ld; i += 32) {
+            const float y = stored(i);
+            sqn = fmaf(y, y, sqn);
+        }
+        sqn = warp_sum(sqn);
+    }
     for (int i = threadIdx.x; i < nch * 32; i += blockDim.x) {
         const int c = i >> 5, l = i & 31;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (i < ld16) v = qv[i];
-        if (F32) {
-            sq[(c * H) * 32 + l] =
-                make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
-        } else {
-            sq[(c * H) * 32 + l] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u),
-                                               __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
-            sq[(c * H + 1) * 32 + l] = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u),
-                                                   __uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u));
-        }
+        const int e0 = i * EPL;
+        float v[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) v[j] = (e0 + j < ld) ? stored(e0 + j) : 0.f;
+        sq[(c * H) * 32 + l] = make_float4(v[0], v[1], v[2], v[3]);
+        if (!F32) sq[(c * H + 1) * 32 + l] = make_float4(v[4], v[5], v[6], v[7]);
     }
+    return sqn;
 }
 
 // dot products of K1_R rows (row pointers rp[], warp-uniform validity va[]) with the staged query;
@@ -101,17 +129,18 @@ __device__ __forceinline__ void rows_dot(const uint4* const (&rp)[K1_R], const b
 
 template <bool F32, int KPL, bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-    k1_scan_topk(const uint4* __restrict__ rows, int64_t n_rows, int ld16, int nch, const uint4* __restrict__ qv,
-                 const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm, int l2,
-                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ part_keys) {
+    k1_scan_topk(const uint4* __restrict__ rows, int64_t n_rows, int dim, int ld, int ld16, int nch,
+                 const float* __restrict__ q_raw, int normalize, const float* __restrict__ row_sqnorm, int l2,
+                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ part_keys, unsigned int* ticket,
+                 K1Out out, int fuse_stage) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
 
-    stage_query<F32>(qv, ld16, nch, sq);
+    const float q_sqn = prepare_query<F32>(q_raw, dim, ld, nch, normalize, l2 != 0, sq);
     __syncthreads();
-    const float l2_bias = l2 ? (1.f - q_sqnorm[0]) : 0.f;
+    const float l2_bias = l2 ? (1.f - q_sqn) : 0.f;
 
     WarpList<KPL> list;
     list.clear();
@@ -189,6 +218,26 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     }
     block_bitonic_desc(sk, K1_WARPS * kp, BetterU64());
     for (int i = threadIdx.x; i < k; i += blockDim.x) part_keys[(int64_t)blockIdx.x * k + i] = sk[i];
+
+    // ---- fused K3: the last CTA to arrive merges all per-CTA lists (no second launch)
+    if (fuse_stage > 0) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            SelectArgs a{part_keys, k, 0, nullptr, 0, 0, (int)gridDim.x, k, k, nullptr, k, out.final_keys,
+                         out.ids, out.scores, out.count};
+            SelectScratch& S = *reinterpret_cast<SelectScratch*>(smem_raw + (size_t)fuse_stage * 8);
+            select_topk_block(a, 0, sk, fuse_stage, S);
+            if (threadIdx.x == 0) *ticket = 0u;
+        }
+    }
 }
 
 // ---- K6a: plain scores (any k): score of every row for one query; masked-out rows get key-0
@@ -196,16 +245,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 // the select step also receives the mask.
 template <bool F32, bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
-    k6_scores(const uint4* __restrict__ rows, int64_t n_rows, int ld16, int nch, const uint4* __restrict__ qv,
-              const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm, int l2,
+    k6_scores(const uint4* __restrict__ rows, int64_t n_rows, int dim, int ld, int ld16, int nch,
+              const float* __restrict__ q_raw, int normalize, const float* __restrict__ row_sqnorm, int l2,
               const uint32_t* __restrict__ mask, float* __restrict__ scores) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    stage_query<F32>(qv, ld16, nch, sq);
+    const float q_sqn = prepare_query<F32>(q_raw, dim, ld, nch, normalize, l2 != 0, sq);
     __syncthreads();
-    const float l2_bias = l2 ? (1.f - q_sqnorm[0]) : 0.f;
+    const float l2_bias = l2 ? (1.f - q_sqn) : 0.f;
     const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
     const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
     const int64_t n_groups = (n_rows + K1_R - 1) / K1_R;
@@ -233,40 +282,46 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     }
 }
 
-static size_t k1_smem_bytes(int dtype, int nch, int k) {
+static size_t k1_smem_bytes(int dtype, int nch, int k, int fuse_stage) {
     size_t q = (size_t)nch * 32 * (dtype == 1 ? 1 : 2) * sizeof(float4);
     size_t m = (size_t)K1_WARPS * next_pow2(k) * sizeof(uint64_t);
-    return q > m ? q : m;
+    size_t f = fuse_stage > 0 ? select_smem_bytes(fuse_stage) : 0;
+    size_t r = q > m ? q : m;
+    return r > f ? r : f;
 }
 
 template <bool F32, int KPL, bool HAS_MASK>
-static cudaError_t k1_launch_t(const void* rows, int64_t n_rows, int ld16, int nch, const void* q,
-                               const float* q_sqnorm, const float* row_sqnorm, int l2, const uint32_t* mask, int k,
-                               uint64_t* part_keys, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t k1_launch_t(const void* rows, int64_t n_rows, int dim, int ld, int ld16, int nch, const float* q_raw,
+                               int normalize, const float* row_sqnorm, int l2, const uint32_t* mask, int k,
+                               uint64_t* part_keys, unsigned int* ticket, K1Out out, int fuse_stage, int grid,
+                               size_t smem, cudaStream_t st) {
     auto kern = k1_scan_topk<F32, KPL, HAS_MASK>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid, K1_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(rows), n_rows, ld16, nch,
-                                          reinterpret_cast<const uint4*>(q), q_sqnorm, row_sqnorm, l2, mask, k,
-                                          part_keys);
+    kern<<<grid, K1_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(rows), n_rows, dim, ld, ld16, nch, q_raw,
+                                          normalize, row_sqnorm, l2, mask, k, part_keys, ticket, out, fuse_stage);
     return cudaGetLastError();
 }
 
-cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
-                      const float* q_sqnorm, const float* row_sqnorm, int metric, const uint32_t* mask, int k,
-                      uint64_t* part_keys, int sm_count, cudaStream_t st) {
-    (void)dim;
+cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
+                      const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
+                      unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st) {
     if (k < 1 || k > 128) return cudaErrorInvalidValue;
+    static_assert(K1_THREADS == SEL_THREADS, "the fused selection runs on the scan's CTA");
     const int ld16 = ld * elem_size(dtype) / 16;
     const int nch = (ld16 + 31) / 32;
     const int grid = k1_parts(sm_count);
-    const size_t smem = k1_smem_bytes(dtype, nch, k);
-    const int l2 = (metric == 2);
+    // fuse the final merge when every per-CTA list fits the in-kernel selection's staging area
+    const int fuse_stage = (ticket && grid * k <= 8192) ? grid * k : 0;
+    if (fused) *fused = fuse_stage > 0;
+    const size_t smem = k1_smem_bytes(dtype, nch, k, fuse_stage);
+    const int l2 = (metric == 2), normalize = (metric == 0);
     const bool f32 = (dtype == 1), big = (k > 32), hm = (mask != nullptr);
-#define YRB_K1(F, K, M) \
-    return k1_launch_t<F, K, M>(rows, n_rows, ld16, nch, q, q_sqnorm, row_sqnorm, l2, mask, k, part_keys, grid, smem, st)
+#define YRB_K1(F, K, M)                                                                                              \
+    return k1_launch_t<F, K, M>(rows, n_rows, dim, ld, ld16, nch, q_raw, normalize, row_sqnorm, l2, mask, k, part_keys, \
+                                ticket, out, fuse_stage, grid, smem, st)
     if (!f32 && !big && !hm) YRB_K1(false, 1, false);
     if (!f32 && !big && hm) YRB_K1(false, 1, true);
     if (!f32 && big && !hm) YRB_K1(false, 4, false);
@@ -278,26 +333,24 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
 #undef YRB_K1
 }
 
-cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
-                          const float* q_sqnorm, const float* row_sqnorm, int metric, const uint32_t* mask,
-                          float* scores, int sm_count, cudaStream_t st) {
-    (void)dim;
+cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
+                          const float* row_sqnorm, int metric, const uint32_t* mask, float* scores, int sm_count,
+                          cudaStream_t st) {
     const int ld16 = ld * elem_size(dtype) / 16;
     const int nch = (ld16 + 31) / 32;
     const size_t smem = (size_t)nch * 32 * (dtype == 1 ? 1 : 2) * sizeof(float4);
-    const int l2 = (metric == 2);
+    const int l2 = (metric == 2), normalize = (metric == 0);
     const uint4* r4 = reinterpret_cast<const uint4*>(rows);
-    const uint4* q4 = reinterpret_cast<const uint4*>(q);
-#define YRB_K6(F, M)                                                                                         \
-    {                                                                                                        \
-        auto kern = k6_scores<F, M>;                                                                         \
-        if (smem > 48 * 1024) {                                                                              \
+#define YRB_K6(F, M)                                                                                            \
+    {                                                                                                           \
+        auto kern = k6_scores<F, M>;                                                                            \
+        if (smem > 48 * 1024) {                                                                                 \
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return e;                                                                  \
-        }                                                                                                    \
-        kern<<<sm_count, K1_THREADS, smem, st>>>(r4, n_rows, ld16, nch, q4, q_sqnorm, row_sqnorm, l2, mask,  \
-                                                 scores);                                                    \
-        return cudaGetLastError();                                                                           \
+            if (e != cudaSuccess) return e;                                                                     \
+        }                                                                                                       \
+        kern<<<sm_count, K1_THREADS, smem, st>>>(r4, n_rows, dim, ld, ld16, nch, q_raw, normalize, row_sqnorm, l2, \
+                                                 mask, scores);                                                 \
+        return cudaGetLastError();                                                                              \
     }
     if (dtype == 1) {
         if (mask) YRB_K6(true, true) else YRB_K6(true, false)

@@ -445,9 +445,10 @@ static cudaError_t launch_gemm(int grid, const CUtensorMap& mq, const CUtensorMa
 
 int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
               int k, const uint32_t* mask, int metric, const float* q_sqnorm, const float* row_sqnorm,
-              uint64_t* out_keys, uint64_t* scratch, int sm_count, cudaStream_t st, int* launches, std::string& err,
+              uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
+              int* launches, std::string& err,
               cudaEvent_t ev_start, cudaEvent_t ev_stop) {
-    (void)capacity; (void)dim; (void)q_sqnorm; (void)row_sqnorm; (void)scratch;
+    (void)capacity; (void)dim; (void)q_sqnorm; (void)row_sqnorm;
     if (metric == YRB_METRIC_L2) {
         err = "K2 handles cosine / dot; euclidean goes through K1";
         return YRB_ERR_UNSUPPORTED;
@@ -515,7 +516,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
                                 nullptr, 0, st));
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
         K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,
-                                    k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st));
+                                    k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st,
+                                    out_ids ? out_ids + (size_t)c0 * k : nullptr,
+                                    out_scores ? out_scores + (size_t)c0 * k : nullptr,
+                                    out_counts ? out_counts + c0 : nullptr));
         *launches += 2;
     }
     return YRB_OK;

@@ -26,10 +26,19 @@ cudaError_t launch_ingest(const float* src, int64_t n, int dim, int ld, int metr
 // ---- K1: single-query scan + in-register top-k.  q = ONE prepared query [ld] in storage dtype.
 // part_keys must hold k1_parts(sm) * k keys.  Writes per-CTA sorted top-k lists.
 int k1_parts(int sm_count);
-cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
-                      const float* q_sqnorm /*device, 1 float*/, const float* row_sqnorm, int metric,
-                      const uint32_t* mask, int k, uint64_t* part_keys, int sm_count,
-                      cudaStream_t st);
+// q_raw: ONE fp32 query [dim] on the device, prepared (normalise + round to the storage dtype, same
+// arithmetic as K5) in the kernel prologue.  When parts*k fits the in-kernel selection, the last CTA to
+// finish also merges the per-CTA lists: final_keys[k] (and ids/scores/count when given) are complete when
+// the launch is; *fused tells the caller.  Otherwise the caller runs launch_select_segments on part_keys.
+struct K1Out {
+    uint64_t* final_keys;  // [k]
+    int64_t* ids;          // optional [k]
+    float* scores;         // optional [k]
+    int32_t* count;        // optional [1]
+};
+cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
+                      const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
+                      unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st);
 
 // ---- K3: merge `parts` sorted k-lists per query ([parts][nq][k]) into [nq][k] (descending keys).
 // scratch must hold parts*nq*k keys when parts*k > 4096 (multi-pass).
@@ -41,7 +50,8 @@ cudaError_t launch_merge_keys(const uint64_t* in, int parts, int nq, int k, uint
 // only keys whose score > thr[q].  k <= 256.
 cudaError_t launch_select_segments(const uint64_t* base, int64_t seg_stride, int64_t q_stride, const int* counts,
                                    int64_t cnt_seg_stride, int64_t cnt_q_stride, int n_seg, int fixed_cnt, int seg_cap,
-                                   const float* thr, int nq, int k, uint64_t* out, cudaStream_t st);
+                                   const float* thr, int nq, int k, uint64_t* out, cudaStream_t st,
+                                   int64_t* ids = nullptr, float* scores = nullptr, int32_t* counts_out = nullptr);
 // keys [nq][k] → ids / scores / counts
 cudaError_t launch_decode(const uint64_t* keys, int nq, int k, int64_t* ids, float* scores,
                           int32_t* counts, cudaStream_t st);
@@ -75,8 +85,8 @@ cudaError_t launch_mask_and(const uint32_t* a, const uint32_t* b, int64_t n_word
                             cudaStream_t st);
 
 // ---- K6: any-k path.  scores fp32 [n_rows] for one query + radix select of the top k.
-cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const void* q,
-                          const float* q_sqnorm, const float* row_sqnorm, int metric,
+cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
+                          const float* row_sqnorm, int metric,
                           const uint32_t* mask, float* scores, int sm_count, cudaStream_t st);
 size_t select_scratch_bytes(int64_t n_rows, int k);
 cudaError_t launch_select(const float* scores, int64_t n_rows, int k, uint64_t* out_keys,
