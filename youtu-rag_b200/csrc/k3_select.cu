@@ -27,7 +27,7 @@ cudaError_t launch_select_segments(const uint64_t* base, int64_t seg_stride, int
                                    int64_t cnt_seg_stride, int64_t cnt_q_stride, int n_seg, int fixed_cnt, int seg_cap,
                                    const float* thr, int nq, int k, uint64_t* out, cudaStream_t st, int64_t* ids,
                                    float* scores, int32_t* counts_out) {
-    if (k < 1 || k > SEL_KMAX) return cudaErrorInvalidValue;
+    if (k < 1 || k > SEL_KMAX || n_seg > SEL_MAX_SEG) return cudaErrorInvalidValue;
     const size_t smem = select_smem_bytes(SEL_STAGE);
     cudaError_t e = cudaFuncSetAttribute(select_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -8,6 +8,7 @@ namespace yrb {
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_KMAX = 256;
+constexpr int SEL_MAX_SEG = 256;  // segments per query (one per CTA of the producing kernel)
 
 struct SelectArgs {
     const uint64_t* base;
@@ -39,6 +40,7 @@ struct SelectScratch {
     int hist[SEL_BINS];
     uint64_t sel[SEL_KMAX];
     uint64_t red[SEL_THREADS / 32 * 2];
+    int seg_cnt[SEL_MAX_SEG];
     int s_n, s_nsel, s_bstar, s_above;
 };
 __host__ __device__ constexpr size_t select_smem_bytes(int stage_keys) {
@@ -62,12 +64,19 @@ __device__ __forceinline__ void select_topk_block(const SelectArgs& a, const int
     }
     __syncthreads();
 
-    // ---- stage (filtered) candidates; count them even when they do not fit
-    for (int seg = warp; seg < a.n_seg; seg += SEL_THREADS / 32) {
-        const int c = seg_count(a, seg, q);
-        const uint64_t* src = a.base + seg * a.seg_stride + q * a.q_stride;
-        for (int i0 = 0; i0 < c; i0 += 32) {
-            const int i = i0 + lane;
+    // ---- stage (filtered) candidates; count them even when they do not fit.
+    // Four threads share a segment so that all segment reads are in flight together (the loop is
+    // latency-bound: segments are short and live in L2).
+    for (int seg = tid; seg < a.n_seg; seg += SEL_THREADS) S.seg_cnt[seg] = seg_count(a, seg, q);
+    __syncthreads();
+    for (int seg0 = 0; seg0 < a.n_seg; seg0 += SEL_THREADS / 4) {
+        const int seg = seg0 + (tid >> 2), r = tid & 3;
+        const int c = seg < a.n_seg ? S.seg_cnt[seg] : 0;
+        const uint64_t* src = a.base + (int64_t)seg * a.seg_stride + (int64_t)q * a.q_stride;
+        int cmax = c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmax = max(cmax, __shfl_xor_sync(YRB_FULL, cmax, o));
+        for (int i = r; i < cmax + r; i += 4) {   // same trip count on every lane of the warp
             uint64_t key = (i < c) ? src[i] : 0ull;
             const bool keep = key != 0ull && (a.thr == nullptr || key_score(key) > thr);
             const unsigned m = __ballot_sync(YRB_FULL, keep);
