@@ -163,3 +163,34 @@ def test_search_is_idempotent_and_sorted_1m():
         o = ox.order_desc_id_asc(best_s, best_ids)[:10]
         assert np.array_equal(a[0][j], best_ids[o]), (a[0][j], best_ids[o])
         np.testing.assert_allclose(a[1][j], best_s[o], rtol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_k6_large_k_any_path(dtype):
+    """k > 128 takes the key-vector + radix-select path; forcing it for small k must agree too."""
+    n, d = 30011, 128
+    x = unit_rows(n, d, 21)
+    x[[100, 20000, 30010]] = x[100]
+    ix = build(x, "cosine", dtype)
+    rows = stored(ix)
+    q = np.concatenate([x[100][None], unit_rows(1, d, 22)])
+    mask = np.random.default_rng(23).random(n) < 0.3
+    for k in (129, 500, 4096):
+        for m in (None, mask):
+            ids, scores, counts = ix.search(q, k, mask=None if m is None else ox.pack_mask(m))
+            for j in range(2):
+                c = int(counts[j])
+                assert c == min(k, n if m is None else int(m.sum()))
+                check_topk(ids[j, :c], scores[j, :c], rows, ox.prepare(q[j], "cosine", dtype)[0], k, "cosine", dtype, mask=m)
+    ix.set_path(native.PATH_K6)
+    a = ix.search(q, 10)
+    ix.set_path(native.PATH_K1)
+    b = ix.search(q, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0][0, :3].tolist() == [100, 20000, 30010]
+    ix.set_path(native.PATH_AUTO)
+    with pytest.raises(native.NativeError):
+        ix.search(q, 5000)                       # above the supported n_results
+    small = build(unit_rows(50, d, 24), "cosine", dtype)
+    ids, _, counts = small.search(q, 4097)       # clamped to the collection size
+    assert int(counts[0]) == 50 and (ids[0, 50:] == -1).all()

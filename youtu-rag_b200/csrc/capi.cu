@@ -76,7 +76,8 @@ struct yrb_index {
     float* d_scores = nullptr;
     int32_t* d_counts = nullptr;
     unsigned int* d_ticket = nullptr;   // K1's last-CTA-done counter
-    float* d_rowscores = nullptr;  // K6, capacity floats
+    uint64_t* d_rowkeys = nullptr;  // K6: one key per row, allocated on first use
+    int64_t rowkeys_cap = 0;
     void* d_select = nullptr;
     size_t select_bytes = 0;
     yrb::WhereProgDev* d_prog = nullptr;
@@ -132,7 +133,6 @@ int ensure_capacity(yrb_index* ix, int64_t want) {
     const size_t ow = (size_t)mask_words(ix->capacity) * 4, nw = (size_t)mask_words(cap) * 4;
     if ((rc = regrow(&ix->d_live, ix->capacity ? ow : 0, nw, true, ix->stream))) return rc;
     if ((rc = regrow(&ix->d_mask, 0, nw, true, ix->stream))) return rc;
-    if ((rc = regrow(&ix->d_rowscores, 0, (size_t)cap * 4, false, ix->stream))) return rc;
     ix->h_live.resize(mask_words(cap), 0u);
     for (auto& kv : ix->cols) {
         Column& c = kv.second;
@@ -405,7 +405,14 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         }
         return YRB_OK;
     }
-    // path 3: score vector + radix select, any k
+    // path 3: key vector + radix select, k <= 4096
+    if (k > 4096) return fail(YRB_ERR_UNSUPPORTED, "k=%d exceeds the largest supported n_results (4096)", k);
+    if (ix->rowkeys_cap < ix->rows) {
+        CK(cudaStreamSynchronize(st));
+        FREE_DEV(ix->d_rowkeys);
+        CK(cudaMalloc(&ix->d_rowkeys, (size_t)ix->capacity * 8));
+        ix->rowkeys_cap = ix->capacity;
+    }
     const size_t need = yrb::select_scratch_bytes(ix->rows, k);
     if (need > ix->select_bytes) {
         CK(cudaStreamSynchronize(st));
@@ -415,9 +422,9 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
     }
     for (int j = 0; j < nq; ++j) {
         CK(yrb::launch_scores(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
-                              ix->metric, mask, ix->d_rowscores, ix->sm_count, st));
-        CK(yrb::launch_select(ix->d_rowscores, ix->rows, k, out_keys + (size_t)j * k, ix->d_select, ix->sm_count, st));
-        ix->launches += 2;
+                              ix->metric, mask, ix->d_rowkeys, ix->sm_count, st));
+        CK(yrb::launch_select(ix->d_rowkeys, ix->rows, k, out_keys + (size_t)j * k, ix->d_select, ix->sm_count, st));
+        ix->launches += 15;
     }
     if (decode) {
         CK(yrb::launch_decode(out_keys, nq, k, ids, scores, counts, st));
@@ -522,7 +529,7 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_DEV(ix->d_sqnorm);
     FREE_DEV(ix->d_live);
     FREE_DEV(ix->d_mask);
-    FREE_DEV(ix->d_rowscores);
+    FREE_DEV(ix->d_rowkeys);
     FREE_DEV(ix->d_select);
     FREE_DEV(ix->d_prog);
     FREE_DEV(ix->d_pass);

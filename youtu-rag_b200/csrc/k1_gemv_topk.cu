@@ -183,28 +183,40 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             consume(rid, va);
         }
     } else {
+        // Passing rows are queued across 64-row mask groups so that every batch carries K1_R rows:
+        // at 10 % selectivity a group holds ~6 rows and per-group batching would leave loads idle.
         const int64_t n_groups = (n_rows + 63) / 64;
         const uint2* mask2 = reinterpret_cast<const uint2*>(mask);
+        int64_t rid[K1_R];
+        bool va[K1_R];
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) {
+            rid[r] = 0;
+            va[r] = false;
+        }
+        int have = 0;  // warp-uniform
         for (int64_t g = gw; g < n_groups; g += tw) {
             const uint2 mw = mask2[g];
             uint64_t m = ((uint64_t)mw.y << 32) | mw.x;
             while (m) {
-                int64_t rid[K1_R];
-                bool va[K1_R];
+                const int64_t row = g * 64 + (__ffsll((long long)m) - 1);
+                m &= m - 1;
+                if (row >= n_rows) continue;
 #pragma unroll
-                for (int r = 0; r < K1_R; ++r) {
-                    va[r] = (m != 0);
-                    rid[r] = 0;
-                    if (va[r]) {
-                        rid[r] = g * 64 + (__ffsll((long long)m) - 1);
-                        m &= m - 1;
-                        va[r] = rid[r] < n_rows;
-                        if (!va[r]) rid[r] = 0;
+                for (int r = 0; r < K1_R; ++r)
+                    if (r == have) {
+                        rid[r] = row;
+                        va[r] = true;
                     }
+                if (++have == K1_R) {
+                    consume(rid, va);
+                    have = 0;
+#pragma unroll
+                    for (int r = 0; r < K1_R; ++r) va[r] = false;
                 }
-                consume(rid, va);
             }
         }
+        if (have) consume(rid, va);
     }
 
     // ---- CTA merge: every warp's first k entries → shared → bitonic → first k to global
@@ -247,7 +259,7 @@ template <bool F32, bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
     k6_scores(const uint4* __restrict__ rows, int64_t n_rows, int dim, int ld, int ld16, int nch,
               const float* __restrict__ q_raw, int normalize, const float* __restrict__ row_sqnorm, int l2,
-              const uint32_t* __restrict__ mask, float* __restrict__ scores) {
+              const uint32_t* __restrict__ mask, uint64_t* __restrict__ keys_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -272,12 +284,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         float acc[K1_R];
         rows_dot<F32>(rp, va, ld16, nch, sq, lane, acc);
         if (lane < K1_R) {
-            float s = -INFINITY;
-            int64_t row = g * K1_R + lane;
+            uint64_t key = 0ull;  // rows the filter hides get the empty key
+            const int64_t row = g * K1_R + lane;
 #pragma unroll
             for (int r = 0; r < K1_R; ++r)
-                if (lane == r && va[r]) s = l2 ? fmaf(2.f, acc[r], l2_bias - row_sqnorm[rid[r]]) : acc[r];
-            if (row < n_rows) scores[row] = s;
+                if (lane == r && va[r])
+                    key = make_key(l2 ? fmaf(2.f, acc[r], l2_bias - row_sqnorm[rid[r]]) : acc[r], (uint32_t)row);
+            if (row < n_rows) keys_out[row] = key;
         }
     }
 }
@@ -334,7 +347,7 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
 }
 
 cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
-                          const float* row_sqnorm, int metric, const uint32_t* mask, float* scores, int sm_count,
+                          const float* row_sqnorm, int metric, const uint32_t* mask, uint64_t* keys_out, int sm_count,
                           cudaStream_t st) {
     const int ld16 = ld * elem_size(dtype) / 16;
     const int nch = (ld16 + 31) / 32;
@@ -349,7 +362,7 @@ cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, 
             if (e != cudaSuccess) return e;                                                                     \
         }                                                                                                       \
         kern<<<sm_count, K1_THREADS, smem, st>>>(r4, n_rows, dim, ld, ld16, nch, q_raw, normalize, row_sqnorm, l2, \
-                                                 mask, scores);                                                 \
+                                                 mask, keys_out);                                               \
         return cudaGetLastError();                                                                              \
     }
     if (dtype == 1) {

@@ -84,12 +84,12 @@ cudaError_t launch_where(const WhereProgDev* prog, int64_t n_rows, const uint32_
 cudaError_t launch_mask_and(const uint32_t* a, const uint32_t* b, int64_t n_words, uint32_t* out,
                             cudaStream_t st);
 
-// ---- K6: any-k path.  scores fp32 [n_rows] for one query + radix select of the top k.
+// ---- K6: any-k path (k <= 4096).  One 64-bit key per row for one query + radix select of the top k.
 cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                           const float* row_sqnorm, int metric,
-                          const uint32_t* mask, float* scores, int sm_count, cudaStream_t st);
+                          const uint32_t* mask, uint64_t* keys_out, int sm_count, cudaStream_t st);
 size_t select_scratch_bytes(int64_t n_rows, int k);
-cudaError_t launch_select(const float* scores, int64_t n_rows, int k, uint64_t* out_keys,
+cudaError_t launch_select(const uint64_t* keys, int64_t n_rows, int k, uint64_t* out_keys,
                           void* scratch, int sm_count, cudaStream_t st);
 
 // ---- K2: batched tcgen05 GEMM + fused top-k epilogue (bf16 storage only).
