@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "../../include/yrb200.h"
 #include "common.cuh"
 #include "k2_batched.h"
@@ -80,6 +82,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each
+// destination CTA's barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -91,6 +116,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrives on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far complete
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -156,7 +187,7 @@ __device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
 template <int QB>
 __global__ void __launch_bounds__(128 + 128 * QB, 1)
     k2_gemm_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows,
-                 int kblocks, int tile_begin, int tile_end, int nq, int k, const uint32_t* __restrict__ mask,
+                 int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                  float* __restrict__ tops, int m_tops) {
     constexpr int S = stages(QB);
@@ -176,7 +207,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), cluster_nctarank());  // one commit-arrival from every CTA of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
@@ -193,10 +224,18 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // Thread-block cluster: the query k-block is the same for every CTA, so each CTA fetches 1/CL of it
+    // and multicasts it to its peers (L2→SM bytes per k-block drop from (QB+1)·16 KiB to (QB/CL+1)·16 KiB).
+    const uint32_t CL = cluster_nctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anything is multicast at them
 
-    // this CTA's tiles: tile_begin + blockIdx.x + i * gridDim.x
+    // this CTA's tiles: tile_begin + blockIdx.x + i * gridDim.x for i < iters — the SAME trip count on every
+    // CTA (cluster peers advance the ring in lockstep); tiles past the end are zero-filled by TMA and masked.
     const int first = tile_begin + (int)blockIdx.x;
     const int step = (int)gridDim.x;
+    const int tile_end = first + iters * step;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -207,9 +246,16 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), SB);
                     const uint32_t dst = smem0 + s * SB;
+                    if (CL == 1) {
 #pragma unroll
-                    for (int qb = 0; qb < QB; ++qb)
-                        tma_load_2d(dst + qb * TILE_BYTES, &tmap_q, full_bar(s), kb * BLOCK_K, qb * BLOCK_Q);
+                        for (int qb = 0; qb < QB; ++qb)
+                            tma_load_2d(dst + qb * TILE_BYTES, &tmap_q, full_bar(s), kb * BLOCK_K, qb * BLOCK_Q);
+                    } else {
+                        // this CTA's slice of the query block: QB*128/CL query rows (the tensor map's box)
+                        const uint32_t piece_rows = (QB * BLOCK_Q) / CL;
+                        tma_load_2d_mcast(dst + crank * piece_rows * (BLOCK_K * 2), &tmap_q, full_bar(s), kb * BLOCK_K,
+                                          (int)(crank * piece_rows), cmask);
+                    }
                     tma_load_2d(dst + QB * TILE_BYTES, &tmap_r, full_bar(s), kb * BLOCK_K, t * BLOCK_R);
                     if (++s == S) {
                         s = 0;
@@ -240,7 +286,8 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                         for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
                             umma_bf16(d, adesc + 2 * k4, bdesc + 2 * k4, IDESC, (kb | k4) != 0);
                     }
-                    umma_commit(empty_bar(s));
+                    if (CL == 1) umma_commit(empty_bar(s));
+                    else umma_commit_mcast(empty_bar(s), cmask);
                     if (++s == S) {
                         s = 0;
                         ph ^= 1;
@@ -349,6 +396,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS));
@@ -406,10 +454,10 @@ void k2_invalidate(K2State*) {}
 int k2_parts(int sm_count) { return sm_count; }
 bool k2_supported(int dtype, int dim, int k) { return dtype == 0 && dim >= 1 && k >= 1 && k <= YRB_FUSED_K_MAX; }
 
-static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows, int ld, std::string& err) {
+static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows, int ld, int box_rows, std::string& err) {
     cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)k2::BLOCK_K, (cuuint32_t)k2::BLOCK_R};
+    cuuint32_t box[2] = {(cuuint32_t)k2::BLOCK_K, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = s->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -431,16 +479,38 @@ static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows
     } while (0)
 
 template <int QB>
-static cudaError_t launch_gemm(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks,
-                               int tile_begin, int tile_end, int nq, int k, const uint32_t* mask, const float* thr,
-                               uint64_t* ck, int* cc, float* tops, int m_tops, cudaStream_t st) {
+static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows,
+                               int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
+                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, 128 + 128 * QB, smem, st>>>(mq, mr, n_rows, kblocks, tile_begin, tile_end, nq, k, mask, thr, ck, cc,
-                                             tops, m_tops);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128 + 128 * QB);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops);
+}
+
+// cluster size for the query multicast: 2 always packs the 148 SMs (74 TPCs); override with YRB_K2_CLUSTER
+static int k2_cluster(int grid) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("YRB_K2_CLUSTER");
+        forced = e ? atoi(e) : 0;
+    }
+    int c = forced > 0 ? forced : 2;
+    while (c > 1 && grid % c) c >>= 1;
+    return c;
 }
 
 int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
@@ -463,42 +533,48 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         }
         s->encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    if (s->slots < sm_count) {
+    const int want_slots = sm_count + 16;  // grids are rounded up to the cluster size
+    if (s->slots < want_slots) {
         if (s->cand_keys) cudaFree(s->cand_keys);
         if (s->cand_cnt) cudaFree(s->cand_cnt);
         if (s->tops) cudaFree(s->tops);
         if (s->thr0) cudaFree(s->thr0);
         s->cand_keys = nullptr; s->cand_cnt = nullptr; s->tops = nullptr; s->thr0 = nullptr;
-        K2CK(cudaMalloc(&s->cand_keys, (size_t)sm_count * k2::MAX_Q * k2::CAP * 8));
-        K2CK(cudaMalloc(&s->cand_cnt, (size_t)sm_count * k2::MAX_Q * 4));
-        K2CK(cudaMalloc(&s->tops, (size_t)sm_count * k2::MAX_TOPS * k2::MAX_Q * 4));
+        K2CK(cudaMalloc(&s->cand_keys, (size_t)want_slots * k2::MAX_Q * k2::CAP * 8));
+        K2CK(cudaMalloc(&s->cand_cnt, (size_t)want_slots * k2::MAX_Q * 4));
+        K2CK(cudaMalloc(&s->tops, (size_t)want_slots * k2::MAX_TOPS * k2::MAX_Q * 4));
         K2CK(cudaMalloc(&s->thr0, (size_t)k2::MAX_Q * 4));
-        s->slots = sm_count;
+        s->slots = want_slots;
     }
     const int kblocks = ld / k2::BLOCK_K;
     const int tiles = (int)((n_rows + k2::BLOCK_R - 1) / k2::BLOCK_R);
     CUtensorMap mr;
-    if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, err)) return YRB_ERR_CUDA;
+    if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, k2::BLOCK_R, err)) return YRB_ERR_CUDA;
 
     for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
         const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
+        // grids are multiples of the cluster size; every CTA runs the same number of tiles
+        int grid = tiles < sm_count ? tiles : sm_count;
+        const int cluster = k2_cluster(sm_count);
+        grid = (grid + cluster - 1) / cluster * cluster;
         CUtensorMap mq;
-        if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld, err))
+        if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld,
+                      QB * k2::BLOCK_Q / cluster, err))
             return YRB_ERR_CUDA;
-        K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)sm_count * k2::MAX_Q * 4, st));
+        K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)s->slots * k2::MAX_Q * 4, st));
         // phase A (sampling): the first tile of each CTA is scored only to publish each query's best
         // scores; thr0 = k-th largest of them is a valid lower bound of the k-th best overall.
-        const int gridA = tiles < sm_count ? tiles : sm_count;
+        const int gridA = tiles < grid ? tiles : grid;   // CTAs that see a real tile
         const int m_tops = (2 * k + gridA - 1) / gridA <= 1 ? 1 : k2::MAX_TOPS;
-        const bool sampled = tiles > 2 * gridA && (int64_t)gridA * m_tops >= k;
+        const bool sampled = tiles > 2 * grid && (int64_t)gridA * m_tops >= k;
         const float* thr = nullptr;
         if (sampled) {
             if (QB == 2)
-                K2CK(launch_gemm<2>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys,
+                K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
                                     s->cand_cnt, s->tops, m_tops, st));
             else
-                K2CK(launch_gemm<1>(gridA, mq, mr, n_rows, kblocks, 0, gridA, nqc, k, mask, nullptr, s->cand_keys,
+                K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
                                     s->cand_cnt, s->tops, m_tops, st));
             k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
             K2CK(cudaGetLastError());
@@ -506,15 +582,16 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             thr = s->thr0;
         }
         // phase B: every tile, with the bound
-        const int gridB = tiles < sm_count ? tiles : sm_count;
+        const int iters = (tiles + grid - 1) / grid;
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
         if (QB == 2)
-            K2CK(launch_gemm<2>(gridB, mq, mr, n_rows, kblocks, 0, tiles, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
-                                nullptr, 0, st));
+            K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
+                                s->cand_cnt, nullptr, 0, st));
         else
-            K2CK(launch_gemm<1>(gridB, mq, mr, n_rows, kblocks, 0, tiles, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
-                                nullptr, 0, st));
+            K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
+                                s->cand_cnt, nullptr, 0, st));
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
+        const int gridB = grid;
         K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,
                                     k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st,
                                     out_ids ? out_ids + (size_t)c0 * k : nullptr,
