@@ -37,16 +37,19 @@ namespace yrb {
 namespace k2 {
 
 constexpr int BLOCK_Q = 128;   // MMA M: queries per query block
-constexpr int BLOCK_R = 128;   // MMA N: corpus rows per tile
+constexpr int BLOCK_R = 256;   // MMA N: corpus rows per tile (N = 256 halves the operand reads per MAC)
 constexpr int BLOCK_K = 64;    // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int CAP = 256;       // candidate slots per (CTA, query)
 constexpr int MAX_Q = 256;     // queries per launch (2 query blocks)
-constexpr int TILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 16 KiB
+constexpr int QTILE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KiB: one query block x one k-block
+constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 32 KiB: one row tile x one k-block
 constexpr int MAX_TOPS = 2;
 
-__host__ __device__ constexpr int stages(int qb) { return qb == 2 ? 4 : 6; }
-__host__ __device__ constexpr int stage_bytes(int qb) { return (qb + 1) * TILE_BYTES; }
+__host__ __device__ constexpr int stages(int qb) { return qb == 2 ? 3 : 4; }
+// accumulator buffers in the 512 TMEM columns: QB=1 → 2 x 256, QB=2 → 1 x 512 (epilogue not overlapped)
+__host__ __device__ constexpr int acc_buffers(int qb) { return qb == 2 ? 1 : 2; }
+__host__ __device__ constexpr int stage_bytes(int qb) { return qb * QTILE_BYTES + RTILE_BYTES; }
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -144,7 +147,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 128
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_R >> 3) << 17) |
                            ((uint32_t)(BLOCK_Q >> 4) << 24);
 
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
     constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
+    constexpr int NBUF = acc_buffers(QB);
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[2 * S + 4];
     __shared__ uint32_t tmem_base_s;
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), cluster_nctarank());  // one commit-arrival from every CTA of the cluster
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NBUF; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 4 * QB);
         }
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
-                     "r"(2 * ACC_COLS));
+                     "r"(NBUF * ACC_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -246,17 +250,14 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), SB);
                     const uint32_t dst = smem0 + s * SB;
-                    if (CL == 1) {
-#pragma unroll
-                        for (int qb = 0; qb < QB; ++qb)
-                            tma_load_2d(dst + qb * TILE_BYTES, &tmap_q, full_bar(s), kb * BLOCK_K, qb * BLOCK_Q);
-                    } else {
-                        // this CTA's slice of the query block: QB*128/CL query rows (the tensor map's box)
-                        const uint32_t piece_rows = (QB * BLOCK_Q) / CL;
+                    // this CTA's slice of the query block: QB*128/CL query rows (= the tensor map's box)
+                    const uint32_t piece_rows = (QB * BLOCK_Q) / CL;
+                    if (CL == 1)
+                        tma_load_2d(dst, &tmap_q, full_bar(s), kb * BLOCK_K, 0);
+                    else
                         tma_load_2d_mcast(dst + crank * piece_rows * (BLOCK_K * 2), &tmap_q, full_bar(s), kb * BLOCK_K,
                                           (int)(crank * piece_rows), cmask);
-                    }
-                    tma_load_2d(dst + QB * TILE_BYTES, &tmap_r, full_bar(s), kb * BLOCK_K, t * BLOCK_R);
+                    tma_load_2d(dst + QB * QTILE_BYTES, &tmap_r, full_bar(s), kb * BLOCK_K, t * BLOCK_R);
                     if (++s == S) {
                         s = 0;
                         ph ^= 1;
@@ -277,10 +278,10 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t a0 = smem0 + s * SB;
-                    const uint64_t bdesc = smem_desc(a0 + QB * TILE_BYTES);
+                    const uint64_t bdesc = smem_desc(a0 + QB * QTILE_BYTES);
 #pragma unroll
                     for (int qb = 0; qb < QB; ++qb) {
-                        const uint64_t adesc = smem_desc(a0 + qb * TILE_BYTES);
+                        const uint64_t adesc = smem_desc(a0 + qb * QTILE_BYTES);
                         const uint32_t d = tmem_base + buf * ACC_COLS + qb * BLOCK_R;
 #pragma unroll
                         for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     }
                 }
                 umma_commit(tfull_bar(buf));
-                if (++buf == 2) {
+                if (++buf == NBUF) {
                     buf = 0;
                     bph ^= 1;
                 }
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
-            if (++buf == 2) {
+            if (++buf == NBUF) {
                 buf = 0;
                 bph ^= 1;
             }
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * ACC_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NBUF * ACC_COLS));
     }
 }
 
