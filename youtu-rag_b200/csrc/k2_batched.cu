@@ -37,7 +37,7 @@ namespace yrb {
 namespace k2 {
 
 constexpr int BLOCK_Q = 128;   // MMA M: queries per query block
-constexpr int BLOCK_R = 256;   // MMA N: corpus rows per tile (N = 256 halves the operand reads per MAC)
+constexpr int BLOCK_R = 128;   // MMA N: corpus rows per tile (256 measured slower: no accumulator double-buffering)
 constexpr int BLOCK_K = 64;    // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int CAP = 256;       // candidate slots per (CTA, query)
@@ -46,9 +46,9 @@ constexpr int QTILE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KiB: one query block x
 constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 32 KiB: one row tile x one k-block
 constexpr int MAX_TOPS = 2;
 
-__host__ __device__ constexpr int stages(int qb) { return qb == 2 ? 3 : 4; }
+__host__ __device__ constexpr int stages(int qb) { return (220 * 1024) / (qb * QTILE_BYTES + RTILE_BYTES); }
 // accumulator buffers in the 512 TMEM columns: QB=1 → 2 x 256, QB=2 → 1 x 512 (epilogue not overlapped)
-__host__ __device__ constexpr int acc_buffers(int qb) { return qb == 2 ? 1 : 2; }
+__host__ __device__ constexpr int acc_buffers(int qb) { return 512 / (qb * BLOCK_R) >= 2 ? 2 : 1; }
 __host__ __device__ constexpr int stage_bytes(int qb) { return qb * QTILE_BYTES + RTILE_BYTES; }
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -94,6 +94,10 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
+}
+// contiguous bulk prefetch into L2 (whole rows: DRAM-page friendly, unlike the 128-byte column slabs of a box)
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -192,7 +196,8 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     k2_gemm_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows,
                  int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
-                 float* __restrict__ tops, int m_tops) {
+                 float* __restrict__ tops, int m_tops, const unsigned char* __restrict__ rows_base, int row_bytes,
+                 int prefetch) {
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
     constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
@@ -247,6 +252,17 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             uint32_t ph = 0;
             for (int t = first; t < tile_end; t += step) {
                 for (int kb = 0; kb < kblocks; ++kb) {
+                    if (prefetch) {
+                        // stream the NEXT tile of this CTA into L2 as whole rows, 1/kblocks of it per k-block
+                        const int64_t nt = (int64_t)t + step;
+                        const int rows_per = (BLOCK_R + kblocks - 1) / kblocks;
+                        const int64_t r0 = nt * BLOCK_R + (int64_t)kb * rows_per;
+                        int64_t r1 = r0 + rows_per;
+                        if (r1 > (nt + 1) * BLOCK_R) r1 = (nt + 1) * BLOCK_R;
+                        if (r1 > n_rows) r1 = n_rows;
+                        if (nt < tile_end && r1 > r0)
+                            prefetch_l2(rows_base + r0 * row_bytes, (uint32_t)((r1 - r0) * row_bytes));
+                    }
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), SB);
                     const uint32_t dst = smem0 + s * SB;
@@ -482,7 +498,8 @@ static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows
 template <int QB>
 static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows,
                                int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
-                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, cudaStream_t st) {
+                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const void* rows_base,
+                               int row_bytes, cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -499,7 +516,10 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops);
+    static int pf = -1;
+    if (pf < 0) pf = getenv("YRB_K2_PREFETCH") ? atoi(getenv("YRB_K2_PREFETCH")) : 1;
+    return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
+                              reinterpret_cast<const unsigned char*>(rows_base), row_bytes, pf);
 }
 
 // cluster size for the query multicast: 2 always packs the 148 SMs (74 TPCs); override with YRB_K2_CLUSTER
@@ -573,10 +593,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (sampled) {
             if (QB == 2)
                 K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, st));
+                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, st));
             else
                 K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, st));
+                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, st));
             k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
             K2CK(cudaGetLastError());
             *launches += 2;
@@ -587,10 +607,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
         if (QB == 2)
             K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, st));
+                                s->cand_cnt, nullptr, 0, rows, ld * 2, st));
         else
             K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, st));
+                                s->cand_cnt, nullptr, 0, rows, ld * 2, st));
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
         const int gridB = grid;
         K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,
