@@ -260,15 +260,18 @@ def run_b200(args):
     l0 = index.launches()
     sampler = ClockSampler(local)
     sampler.start()
+    # steps are issued back to back: scan on `st`, exchange + merge on the searcher's comm stream, so the
+    # exchange of step i overlaps the scan of step i+1 (independent queries).  The timed region starts on the
+    # scan stream and ends when the LAST step's merged result is complete on the comm stream.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
     for i in range(args.steps):
         step_device(args.warmup + i)
-    e1.record(st)
+    e1.record(searcher.comm_stream)
     barrier()
     clocks = sampler.finish()
     ms_total = e0.elapsed_time(e1)
-    launches = index.launches() - l0 + args.steps  # + the K3 global merge per step
+    launches = index.launches() - l0 + (args.steps if world > 1 else 0)  # + the K3 global merge per step
     kern_ms, kern_n = index.profile_read()
     index.profile(False)
     t = torch.tensor([ms_total], device=dev)
@@ -285,7 +288,7 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         a.record(st)
         step_device(i)
-        b.record(st)
+        b.record(searcher.comm_stream)
         b.synchronize()
         lat.append(a.elapsed_time(b))
     lat.sort()

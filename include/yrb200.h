@@ -145,6 +145,12 @@ YRB_API int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k,
 YRB_API int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k,
                             const uint32_t* dev_mask, uint64_t* dev_out_keys, void* stream);
 
+/* Same, but decoded on the device: out_ids [nq*k] (-1 padding), out_scores [nq*k], out_counts [nq]
+ * (all device pointers).  Single-GPU serving path: a single-query search is ONE kernel launch. */
+YRB_API int yrb_index_search_device_ids(yrb_index* ix, const float* dev_queries, int nq, int k,
+                                        const uint32_t* dev_mask, int64_t* dev_out_ids, float* dev_out_scores,
+                                        int32_t* dev_out_counts, void* stream);
+
 /* The top-k merge collective's local step (kernel K3): `parts` sorted lists of k keys
  * per query, laid out [parts][nq][k] (the NCCL all-gather buffer, part p = rank p's shard) →
  * out_ids (global id = row_base[p] + local row), out_scores, out_counts.  All device pointers. */

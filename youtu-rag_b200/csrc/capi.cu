@@ -357,8 +357,9 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
 
 // raw fp32 queries [nq, dim] on the device → nq*k keys (and, when `decode`, ix->d_ids/d_scores/d_counts).
 // K1 prepares the query in its own prologue; K2 needs the prepared bf16 matrix (K5 launch).
-int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, uint64_t* out_keys, bool decode,
-                cudaStream_t st) {
+int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, uint64_t* out_keys, int64_t* ids,
+                float* scores, int32_t* counts, cudaStream_t st) {
+    const bool decode = ids != nullptr;
     int path = ix->path;
     if (path == 0) {
         if (k > YRB_FUSED_K_MAX) path = 3;
@@ -369,9 +370,6 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage, cosine/dot and k <= %d", YRB_FUSED_K_MAX);
     if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
         return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
-    int64_t* ids = decode ? ix->d_ids : nullptr;
-    float* scores = decode ? ix->d_scores : nullptr;
-    int32_t* counts = decode ? ix->d_counts : nullptr;
     if (path == 2) {
         CK(yrb::launch_ingest(dev_q, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
         int launches = 1;
@@ -802,7 +800,7 @@ int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const y
     }
     const uint32_t* m = nullptr;
     rc = resolve_mask(ix, w, dev_extra, &m, st, false);
-    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, ix->d_keys, true, st);
+    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, ix->d_keys, ix->d_ids, ix->d_scores, ix->d_counts, st);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -843,7 +841,24 @@ int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int
     if ((rc = ensure_scratch(ix, nq, k))) return rc;
     const uint32_t* m = nullptr;
     if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
-    return scan_select(ix, dev_queries, nq, k, m, dev_out_keys, false, st);
+    return scan_select(ix, dev_queries, nq, k, m, dev_out_keys, nullptr, nullptr, nullptr, st);
+}
+
+int yrb_index_search_device_ids(yrb_index* ix, const float* dev_queries, int nq, int k, const uint32_t* dev_mask,
+                                int64_t* dev_out_ids, float* dev_out_scores, int32_t* dev_out_counts, void* stream) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (nq < 1 || !dev_queries || !dev_out_ids || !dev_out_scores || !dev_out_counts)
+        return fail(YRB_ERR_INVALID, "bad arguments");
+    if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (k > ix->rows) return fail(YRB_ERR_INVALID, "k=%d exceeds rows=%lld (device variant does not clamp)", k, (long long)ix->rows);
+    if ((rc = ensure_scratch(ix, nq, k))) return rc;
+    const uint32_t* m = nullptr;
+    if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
+    return scan_select(ix, dev_queries, nq, k, m, ix->d_keys, dev_out_ids, dev_out_scores, dev_out_counts, st);
 }
 
 int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int nq, int k, const int64_t* dev_row_base,

@@ -32,6 +32,7 @@ EXPORTS = (
     "yrb_index_reserve", "yrb_index_count", "yrb_index_info", "yrb_index_append_host_f32",
     "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_set_live", "yrb_index_clear",
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_device",
+    "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
     "yrb_index_profile_read",
 )
@@ -86,6 +87,7 @@ def lib() -> C.CDLL:
     L.yrb_index_where.argtypes = [vp, C.POINTER(Where), vp, C.POINTER(i64)]
     L.yrb_index_search.argtypes = [vp, vp, i32, i32, C.POINTER(Where), vp, vp, vp, vp]
     L.yrb_index_search_device.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.yrb_index_search_device_ids.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_index_set_path.argtypes = [vp, i32]
     L.yrb_index_stats.argtypes = [vp, C.POINTER(i64)]
@@ -226,6 +228,11 @@ class Index:
 
     def search_device(self, dev_queries: int, nq: int, k: int, dev_mask: int, dev_out_keys: int, stream: int = 0):
         _ck(lib().yrb_index_search_device(self._h, dev_queries, nq, k, dev_mask or None, dev_out_keys, stream or None))
+
+    def search_device_ids(self, dev_queries: int, nq: int, k: int, dev_mask: int, dev_ids: int, dev_scores: int,
+                          dev_counts: int, stream: int = 0):
+        _ck(lib().yrb_index_search_device_ids(self._h, dev_queries, nq, k, dev_mask or None, dev_ids, dev_scores,
+                                              dev_counts, stream or None))
 
     def set_path(self, path: int) -> None:
         _ck(lib().yrb_index_set_path(self._h, path))

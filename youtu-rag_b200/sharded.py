@@ -31,57 +31,81 @@ def shard_bounds(n_rows: int, world: int) -> list[int]:
 
 
 class ShardedSearcher:
-    def __init__(self, index: native.Index | None, row_base: list[int], group=None):
+    """Search over a row-sharded collection.  Two CUDA streams: the local scan runs on `stream`, the
+    exchange (all-gather + K3 merge) on `comm_stream`, with `depth` result slots, so when searches
+    are issued back to back the exchange of search i overlaps the scan of search i+1 (independent
+    queries; the latency of one search is unchanged).  With world == 1 there is no exchange and the
+    scan kernel writes ids/scores itself (one launch per single-query search)."""
+
+    def __init__(self, index: native.Index | None, row_base: list[int], group=None, depth: int = 2):
         self.index = index
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         assert len(row_base) == self.world + 1
         self.row_base = list(row_base)
+        self.depth = max(1, depth)
+        self._turn = 0
         self._cuda = index is not None
         if self._cuda:
             self.device = torch.device("cuda", index.device)
             self._base_dev = torch.tensor(self.row_base[:-1], dtype=torch.int64, device=self.device)
-            # a real (non-NULL) stream: the C ABI treats a NULL stream as "the index's own stream"
+            # real (non-NULL) streams: the C ABI treats a NULL stream as "the index's own stream"
             self.stream = torch.cuda.Stream(self.device)
+            self.comm_stream = torch.cuda.Stream(self.device) if self.world > 1 else self.stream
         self._bufs = {}
 
     def _buffers(self, nq: int, k: int):
         key = (nq, k)
         if key not in self._bufs:
             dev = self.device
-            self._bufs[key] = dict(
+            self._bufs[key] = [dict(
                 local=torch.zeros(nq * k, dtype=torch.int64, device=dev),
                 gathered=torch.zeros(self.world * nq * k, dtype=torch.int64, device=dev),
                 ids=torch.empty(nq * k, dtype=torch.int64, device=dev),
                 scores=torch.empty(nq * k, dtype=torch.float32, device=dev),
-                counts=torch.empty(nq, dtype=torch.int32, device=dev))
+                counts=torch.empty(nq, dtype=torch.int32, device=dev),
+                scanned=torch.cuda.Event(), merged=torch.cuda.Event()) for _ in range(self.depth)]
         return self._bufs[key]
 
     def search_device(self, dev_queries: torch.Tensor, k: int, dev_mask: torch.Tensor | None = None):
         """queries fp32 [nq, dim] on this rank's GPU (identical on all ranks).  Returns device tensors
-        (ids [nq,k] global row ids, scores [nq,k], counts [nq]); asynchronous on `self.stream` (inputs must
-        be ready before the call; consumers synchronise with `self.stream`)."""
+        (ids [nq,k] global row ids, scores [nq,k], counts [nq]) that are complete once `comm_stream`
+        reaches this point (inputs must be ready before the call).  The returned tensors are reused
+        `depth` searches later."""
         nq = dev_queries.shape[0]
-        b = self._buffers(nq, k)
-        with torch.cuda.stream(self.stream):
-            st = self.stream.cuda_stream
-            self.index.search_device(dev_queries.data_ptr(), nq, k, dev_mask.data_ptr() if dev_mask is not None else 0,
-                                     b["local"].data_ptr(), st)
-            if self.world > 1:
-                dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
-                src = b["gathered"]
-            else:
-                src = b["local"]
-            native.merge_topk_device(self.index.device, src.data_ptr(), self.world, nq, k, self._base_dev.data_ptr(),
-                                     b["ids"].data_ptr(), b["scores"].data_ptr(), b["counts"].data_ptr(), st)
+        slots = self._buffers(nq, k)
+        b = slots[self._turn % self.depth]
+        self._turn += 1
+        mptr = dev_mask.data_ptr() if dev_mask is not None else 0
+        if self.world == 1:
+            self.index.search_device_ids(dev_queries.data_ptr(), nq, k, mptr, b["ids"].data_ptr(), b["scores"].data_ptr(),
+                                         b["counts"].data_ptr(), self.stream.cuda_stream)
+            return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
+        # the slot's previous exchange must have consumed `local` before the scan overwrites it
+        self.stream.wait_event(b["merged"])
+        self.index.search_device(dev_queries.data_ptr(), nq, k, mptr, b["local"].data_ptr(), self.stream.cuda_stream)
+        b["scanned"].record(self.stream)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(b["scanned"])
+            dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+            native.merge_topk_device(self.index.device, b["gathered"].data_ptr(), self.world, nq, k,
+                                     self._base_dev.data_ptr(), b["ids"].data_ptr(), b["scores"].data_ptr(),
+                                     b["counts"].data_ptr(), self.comm_stream.cuda_stream)
+            b["merged"].record(self.comm_stream)
         return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
+
+    def synchronize(self) -> None:
+        self.stream.synchronize()
+        self.comm_stream.synchronize()
 
     def search(self, queries: np.ndarray, k: int, dev_mask: torch.Tensor | None = None):
         """Host in / host out (pinned staging is torch's)."""
         with torch.cuda.stream(self.stream):
             q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
-            ids, scores, counts = self.search_device(q, k, dev_mask)
+        self.stream.synchronize()
+        ids, scores, counts = self.search_device(q, k, dev_mask)
+        with torch.cuda.stream(self.comm_stream):
             out = ids.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
         return out
 
