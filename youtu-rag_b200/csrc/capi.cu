@@ -508,8 +508,8 @@ int yrb_index_create(yrb_index** out, int device, int dim, int metric, int stora
     CKB(cudaMalloc(&ix->d_prog, sizeof(yrb::WhereProgDev)));
     CKB(cudaMallocHost(&ix->h_prog, sizeof(yrb::WhereProgDev)));
     CKB(cudaMalloc(&ix->d_pass, 8));
-    CKB(cudaMalloc(&ix->d_ticket, 4));
-    CKB(cudaMemset(ix->d_ticket, 0, 4));
+    CKB(cudaMalloc(&ix->d_ticket, 8));  // [0] CTAs done, [1] next chunk
+    CKB(cudaMemset(ix->d_ticket, 0, 8));
 #undef CKB
     ix->k2 = yrb::k2_create();
     rc = ensure_capacity(ix, std::max<int64_t>(reserve_rows, 1));

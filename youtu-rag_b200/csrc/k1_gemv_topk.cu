@@ -23,6 +23,7 @@ constexpr int K1_THREADS = 512;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_R = 4;   // rows per batch
 constexpr int K1_CU = 4;  // chunks per unrolled step
+constexpr int K1_CHUNK = 64;  // rows per dynamically scheduled work item (= one 64-bit mask group)
 
 int k1_parts(int sm_count) { return sm_count; }
 
@@ -169,18 +170,34 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         }
     };
 
+    // Rows are handed out dynamically in chunks of 64 (128 KiB at 1024-d bf16): the first chunk of a warp is
+    // its global warp index, further chunks come from an atomic counter.  A CTA that starts late (another
+    // kernel holds its SM) or an SM that runs slower simply takes fewer chunks, so the scan has no tail.
+    const int64_t n_chunks = (n_rows + K1_CHUNK - 1) / K1_CHUNK;
+    auto grab = [&]() -> int64_t {
+        unsigned int c = 0;
+        if (lane == 0) c = atomicAdd(ticket + 1, 1u);
+        return (int64_t)__shfl_sync(YRB_FULL, c, 0) + tw;
+    };
     if (!HAS_MASK) {
-        const int64_t n_groups = (n_rows + K1_R - 1) / K1_R;
-        for (int64_t g = gw; g < n_groups; g += tw) {
-            int64_t rid[K1_R];
-            bool va[K1_R];
+        int64_t c = gw;
+        while (c < n_chunks) {
+            const int64_t next = grab();
+            const int64_t r_begin = c * K1_CHUNK;
+#pragma unroll 1
+            for (int b = 0; b < K1_CHUNK / K1_R; ++b) {
+                int64_t rid[K1_R];
+                bool va[K1_R];
 #pragma unroll
-            for (int r = 0; r < K1_R; ++r) {
-                rid[r] = g * K1_R + r;
-                va[r] = rid[r] < n_rows;
-                if (!va[r]) rid[r] = 0;
+                for (int r = 0; r < K1_R; ++r) {
+                    rid[r] = r_begin + b * K1_R + r;
+                    va[r] = rid[r] < n_rows;
+                    if (!va[r]) rid[r] = 0;
+                }
+                if (!va[0]) break;
+                consume(rid, va);
             }
-            consume(rid, va);
+            c = next;
         }
     } else {
         // Passing rows are queued across 64-row mask groups so that every batch carries K1_R rows:
@@ -195,7 +212,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             va[r] = false;
         }
         int have = 0;  // warp-uniform
-        for (int64_t g = gw; g < n_groups; g += tw) {
+        int64_t g = gw;
+        while (g < n_groups) {
+            const int64_t next = grab();
             const uint2 mw = mask2[g];
             uint64_t m = ((uint64_t)mw.y << 32) | mw.x;
             while (m) {
@@ -215,6 +234,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                     for (int r = 0; r < K1_R; ++r) va[r] = false;
                 }
             }
+            g = next;
         }
         if (have) consume(rid, va);
     }
@@ -232,22 +252,25 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     for (int i = threadIdx.x; i < k; i += blockDim.x) part_keys[(int64_t)blockIdx.x * k + i] = sk[i];
 
     // ---- fused K3: the last CTA to arrive merges all per-CTA lists (no second launch)
-    if (fuse_stage > 0) {
+    {
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int t = atomicAdd(ticket, 1u);
             s_last = (t == gridDim.x - 1);
+            if (s_last) {
+                ticket[0] = 0u;  // every CTA has left the scan: rearm both counters for the next launch
+                ticket[1] = 0u;
+            }
         }
         __syncthreads();
-        if (s_last) {
+        if (s_last && fuse_stage > 0) {
             __threadfence();
             SelectArgs a{part_keys, k, 0, nullptr, 0, 0, (int)gridDim.x, k, k, nullptr, k, out.final_keys,
                          out.ids, out.scores, out.count};
             SelectScratch& S = *reinterpret_cast<SelectScratch*>(smem_raw + (size_t)fuse_stage * 8);
             select_topk_block(a, 0, sk, fuse_stage, S);
-            if (threadIdx.x == 0) *ticket = 0u;
         }
     }
 }
@@ -327,7 +350,7 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
     const int nch = (ld16 + 31) / 32;
     const int grid = k1_parts(sm_count);
     // fuse the final merge when every per-CTA list fits the in-kernel selection's staging area
-    const int fuse_stage = (ticket && grid * k <= 8192) ? grid * k : 0;
+    const int fuse_stage = (grid * k <= 8192) ? grid * k : 0;
     if (fused) *fused = fuse_stage > 0;
     const size_t smem = k1_smem_bytes(dtype, nch, k, fuse_stage);
     const int l2 = (metric == 2), normalize = (metric == 0);
