@@ -13,6 +13,8 @@
 // Algorithmic bytes per search: sel·N·ld·esize + N/8 (mask) + ld·esize (query) + parts·k·8.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "select.cuh"
@@ -25,7 +27,14 @@ constexpr int K1_R = 4;   // rows per batch
 constexpr int K1_CU = 4;  // chunks per unrolled step
 constexpr int K1_CHUNK = 64;  // rows per dynamically scheduled work item (= one 64-bit mask group)
 
-int k1_parts(int sm_count) { return sm_count; }
+// CTAs of the scan.  YRB_K1_RESERVE_SMS leaves that many SMs free so that kernels of another stream
+// (the NCCL exchange of the previous search) can run beside the persistent scan.
+int k1_parts(int sm_count) {
+    static int reserve = -1;
+    if (reserve < 0) reserve = getenv("YRB_K1_RESERVE_SMS") ? atoi(getenv("YRB_K1_RESERVE_SMS")) : 0;
+    const int g = sm_count - reserve;
+    return g > 0 ? g : 1;
+}
 
 template <bool F32>
 __device__ __forceinline__ float dot_chunk(uint4 v, float4 qa, float4 qb, float acc) {
@@ -174,15 +183,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     // its global warp index, further chunks come from an atomic counter.  A CTA that starts late (another
     // kernel holds its SM) or an SM that runs slower simply takes fewer chunks, so the scan has no tail.
     const int64_t n_chunks = (n_rows + K1_CHUNK - 1) / K1_CHUNK;
-    auto grab = [&]() -> int64_t {
-        unsigned int c = 0;
-        if (lane == 0) c = atomicAdd(ticket + 1, 1u);
-        return (int64_t)__shfl_sync(YRB_FULL, c, 0) + tw;
-    };
+    // the atomic is issued when a chunk starts and its result is only broadcast when the chunk is done,
+    // so its round trip hides behind the chunk's loads
+    auto grab_issue = [&]() -> unsigned int { return lane == 0 ? atomicAdd(ticket + 1, 1u) : 0u; };
+    auto grab_get = [&](unsigned int c) -> int64_t { return (int64_t)__shfl_sync(YRB_FULL, c, 0) + tw; };
     if (!HAS_MASK) {
         int64_t c = gw;
         while (c < n_chunks) {
-            const int64_t next = grab();
+            const unsigned int nx = grab_issue();
             const int64_t r_begin = c * K1_CHUNK;
 #pragma unroll 1
             for (int b = 0; b < K1_CHUNK / K1_R; ++b) {
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 if (!va[0]) break;
                 consume(rid, va);
             }
-            c = next;
+            c = grab_get(nx);
         }
     } else {
         // Passing rows are queued across 64-row mask groups so that every batch carries K1_R rows:
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         int have = 0;  // warp-uniform
         int64_t g = gw;
         while (g < n_groups) {
-            const int64_t next = grab();
+            const unsigned int nx = grab_issue();
             const uint2 mw = mask2[g];
             uint64_t m = ((uint64_t)mw.y << 32) | mw.x;
             while (m) {
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                     for (int r = 0; r < K1_R; ++r) va[r] = false;
                 }
             }
-            g = next;
+            g = grab_get(nx);
         }
         if (have) consume(rid, va);
     }

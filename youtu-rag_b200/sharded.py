@@ -52,7 +52,7 @@ class ShardedSearcher:
             self._base_dev = torch.tensor(self.row_base[:-1], dtype=torch.int64, device=self.device)
             # real (non-NULL) streams: the C ABI treats a NULL stream as "the index's own stream"
             self.stream = torch.cuda.Stream(self.device)
-            self.comm_stream = torch.cuda.Stream(self.device) if self.world > 1 else self.stream
+            self.comm_stream = torch.cuda.Stream(self.device, priority=-1) if self.world > 1 else self.stream
         self._bufs = {}
 
     def _buffers(self, nq: int, k: int):
