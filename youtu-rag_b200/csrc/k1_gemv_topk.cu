@@ -179,33 +179,28 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         }
     };
 
-    // Rows are handed out dynamically in chunks of 64 (128 KiB at 1024-d bf16): the first chunk of a warp is
-    // its global warp index, further chunks come from an atomic counter.  A CTA that starts late (another
-    // kernel holds its SM) or an SM that runs slower simply takes fewer chunks, so the scan has no tail.
-    const int64_t n_chunks = (n_rows + K1_CHUNK - 1) / K1_CHUNK;
+    // Masked scans hand out 64-row mask groups dynamically (first group = the warp's global index, further
+    // ones from an atomic counter): the number of passing rows per group varies, so static dealing would
+    // leave some warps with more work.
     // the atomic is issued when a chunk starts and its result is only broadcast when the chunk is done,
     // so its round trip hides behind the chunk's loads
     auto grab_issue = [&]() -> unsigned int { return lane == 0 ? atomicAdd(ticket + 1, 1u) : 0u; };
     auto grab_get = [&](unsigned int c) -> int64_t { return (int64_t)__shfl_sync(YRB_FULL, c, 0) + tw; };
     if (!HAS_MASK) {
-        int64_t c = gw;
-        while (c < n_chunks) {
-            const unsigned int nx = grab_issue();
-            const int64_t r_begin = c * K1_CHUNK;
-#pragma unroll 1
-            for (int b = 0; b < K1_CHUNK / K1_R; ++b) {
-                int64_t rid[K1_R];
-                bool va[K1_R];
+        // dense: groups of K1_R rows dealt round-robin to all warps of the grid.  Every warp then sweeps the
+        // same moving window of the matrix (best DRAM locality) and the tail imbalance is one 4-row group;
+        // measured 8-20 % faster than 64-row dynamic chunks, whose quantisation costs more than it saves.
+        const int64_t n_groups4 = (n_rows + K1_R - 1) / K1_R;
+        for (int64_t g = gw; g < n_groups4; g += tw) {
+            int64_t rid[K1_R];
+            bool va[K1_R];
 #pragma unroll
-                for (int r = 0; r < K1_R; ++r) {
-                    rid[r] = r_begin + b * K1_R + r;
-                    va[r] = rid[r] < n_rows;
-                    if (!va[r]) rid[r] = 0;
-                }
-                if (!va[0]) break;
-                consume(rid, va);
+            for (int r = 0; r < K1_R; ++r) {
+                rid[r] = g * K1_R + r;
+                va[r] = rid[r] < n_rows;
+                if (!va[r]) rid[r] = 0;
             }
-            c = grab_get(nx);
+            consume(rid, va);
         }
     } else {
         // Passing rows are queued across 64-row mask groups so that every batch carries K1_R rows:
