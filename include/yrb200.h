@@ -139,6 +139,14 @@ YRB_API int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k,
                      const uint32_t* mask, int64_t* out_ids, float* out_scores,
                      int32_t* out_counts);
 
+/* One filter per query (wheres[q] may be NULL = no filter): the batched form of the reference's
+ * per-column searches (utu/tools/text2sql/unified_schemalink_valuelink.py:289-303 loops
+ * CourseSearcher.search, chroma_retrical_text2sql.py:148-194, one filtered search per column with
+ * the same query vector).  Identical programs (same pointer) are evaluated once. */
+YRB_API int yrb_index_search_multi(yrb_index* ix, const float* queries, int nq, int k,
+                                   const yrb_where* const* wheres, int64_t* out_ids, float* out_scores,
+                                   int32_t* out_counts);
+
 /* All-device variant for resident inputs (bench `value`, sharded search): queries fp32 [nq, dim]
  * on the device, mask device words or NULL, outputs = nq*k packed 64-bit selection keys
  * (see yrb_key_*), best first, 0 = empty slot.  Asynchronous on `stream`. */

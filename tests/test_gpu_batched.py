@@ -117,3 +117,46 @@ def test_auto_path_uses_k2_for_batches_and_store_batch_api():
         single = asyncio.run(s.search(qs[j].tolist(), top_k=5, filters={"source": {"$in": ["file0.pdf", "file3.pdf"]}}))
         assert [c.id for c, _ in batch[j]] == [c.id for c, _ in single]
         np.testing.assert_allclose([sc for _, sc in batch[j]], [sc for _, sc in single], atol=3e-6)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_batched_euclidean(dtype):
+    n, d, nq = 20000, 256, 40
+    x = unit_rows(n, d, 31) * np.random.default_rng(32).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    ix = native.Index(d, "euclidean", dtype, 0, 0)
+    ix.append(x)
+    rows = ix.read_rows(np.arange(n))
+    qs = unit_rows(nq, d, 33)
+    ids, scores, counts = ix.search(qs, 10)          # bf16 → K2 with the euclidean epilogue; f32 → K1 loop
+    for j in (0, 17, 39):
+        check_topk(ids[j], scores[j], rows, ox.prepare(qs[j], "euclidean", dtype)[0], 10, "euclidean", dtype, tie_eps=2e-5)
+
+
+@pytest.mark.parametrize("nq", [3, 24])
+def test_per_query_filters(nq):
+    """One metadata filter per query: K1 loop for small batches, K2 with per-query masks for large ones."""
+    import asyncio
+
+    from oracle import where_eval as ow
+    from youtu_rag_b200 import B200VectorStore, Chunk, VectorStoreConfig
+
+    n, d = 6000, 64
+    x = unit_rows(n, d, 41)
+    metas = [{"table_name": f"t{i % 7}", "column_name": f"c{i % 3}", "type": "column_value", "v": i % 11} for i in range(n)]
+    s = B200VectorStore(VectorStoreConfig(collection_name="pq"))
+    asyncio.run(s.add_chunks([Chunk(id=f"r{i}", document_id="d", content="", chunk_index=i, metadata=metas[i],
+                                    embedding=x[i].tolist()) for i in range(n)]))
+    q = unit_rows(1, d, 42)[0]
+    filters = [None if j % 5 == 4 else {"$and": [{"type": "column_value"}, {"table_name": f"t{j % 7}"}, {"column_name": f"c{j % 3}"}]}
+               for j in range(nq)]
+    filters[1] = {"v": {"$gte": 9}}
+    got = asyncio.run(s.search_batch(np.tile(q, (nq, 1)), top_k=3, filters=filters))
+    rows = s.index.read_rows(np.arange(n))
+    full_meta = [{"document_id": "d", "chunk_index": i, **metas[i]} for i in range(n)]
+    for j in range(nq):
+        mask = ow.eval_where(filters[j], full_meta)
+        ids = np.array([int(c.id[1:]) for c, _ in got[j]])
+        sc = np.array([v for _, v in got[j]])
+        check_topk(ids, sc, rows, ox.prepare(q, "cosine", "bf16")[0], 3, "cosine", "bf16", mask=mask)
+        single = asyncio.run(s.search(q.tolist(), top_k=3, filters=filters[j]))
+        assert [c.id for c, _ in single] == [c.id for c, _ in got[j]]

@@ -82,6 +82,11 @@ struct yrb_index {
     size_t select_bytes = 0;
     yrb::WhereProgDev* d_prog = nullptr;
     yrb::WhereProgDev* h_prog = nullptr;  // pinned
+    yrb::WhereProgDev* d_progs = nullptr;  // per-query filters of a batch
+    yrb::WhereProgDev* h_progs = nullptr;
+    size_t progs_cap = 0;
+    uint32_t* d_qmasks = nullptr;          // [nq][mask_words]
+    size_t qmasks_bytes = 0;
     unsigned long long* d_pass = nullptr;
     // pinned staging
     float* h_q = nullptr;
@@ -303,6 +308,50 @@ int resolve_mask(yrb_index* ix, const yrb_where* w, const uint32_t* dev_extra, c
     return YRB_OK;
 }
 
+// per-query filters → ix->d_qmasks [nq][mask_words]; programs are deduplicated by pointer
+int resolve_masks_multi(yrb_index* ix, const yrb_where* const* wheres, int nq, const uint32_t* dev_extra,
+                        const uint32_t** out, int64_t* out_stride, cudaStream_t st) {
+    const int64_t words = mask_words(ix->rows);
+    const size_t need = (size_t)nq * words * 4;
+    if (need > ix->qmasks_bytes) {
+        CK(cudaStreamSynchronize(st));
+        FREE_DEV(ix->d_qmasks);
+        CK(cudaMalloc(&ix->d_qmasks, need));
+        ix->qmasks_bytes = need;
+    }
+    if ((int)ix->progs_cap < nq) {
+        CK(cudaStreamSynchronize(st));
+        FREE_DEV(ix->d_progs);
+        FREE_HOST(ix->h_progs);
+        CK(cudaMalloc(&ix->d_progs, (size_t)nq * sizeof(yrb::WhereProgDev)));
+        CK(cudaMallocHost(&ix->h_progs, (size_t)nq * sizeof(yrb::WhereProgDev)));
+        ix->progs_cap = nq;
+    }
+    const uint32_t* live = ix->n_dead > 0 ? ix->d_live : nullptr;
+    yrb::WhereProgDev* saved = ix->h_prog;
+    yrb_where all = {nullptr, 0, nullptr, 0, nullptr, 0};
+    for (int j = 0; j < nq; ++j) {
+        uint32_t* dst = ix->d_qmasks + (size_t)j * words;
+        int dup = -1;
+        for (int i = 0; i < j && dup < 0; ++i)
+            if (wheres[i] == wheres[j]) dup = i;
+        if (dup >= 0) {
+            CK(cudaMemcpyAsync(dst, ix->d_qmasks + (size_t)dup * words, (size_t)words * 4, cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        ix->h_prog = ix->h_progs + j;  // build_prog writes into ix->h_prog
+        int rc = build_prog(ix, wheres[j] ? wheres[j] : &all);
+        ix->h_prog = saved;
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ix->d_progs + j, ix->h_progs + j, sizeof(yrb::WhereProgDev), cudaMemcpyHostToDevice, st));
+        CK(yrb::launch_where(ix->d_progs + j, ix->rows, live, dev_extra, dst, nullptr, st));
+        ix->launches++;
+    }
+    *out = ix->d_qmasks;
+    *out_stride = words;
+    return YRB_OK;
+}
+
 int prof_flush(yrb_index* ix) {
     for (size_t i = 0; i + 1 < ix->prof_used; i += 2) {
         CK(cudaEventSynchronize(ix->prof_ev[i + 1]));
@@ -357,17 +406,17 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
 
 // raw fp32 queries [nq, dim] on the device → nq*k keys (and, when `decode`, ix->d_ids/d_scores/d_counts).
 // K1 prepares the query in its own prologue; K2 needs the prepared bf16 matrix (K5 launch).
-int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, uint64_t* out_keys, int64_t* ids,
-                float* scores, int32_t* counts, cudaStream_t st) {
+int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, int64_t mask_q_stride,
+                uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st) {
     const bool decode = ids != nullptr;
     int path = ix->path;
     if (path == 0) {
         if (k > YRB_FUSED_K_MAX) path = 3;
-        else if (nq >= 8 && ix->metric != YRB_METRIC_L2 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
+        else if (nq >= 8 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
         else path = 1;
     }
-    if (path == 2 && (ix->metric == YRB_METRIC_L2 || !yrb::k2_supported(ix->dtype, ix->dim, k)))
-        return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage, cosine/dot and k <= %d", YRB_FUSED_K_MAX);
+    if (path == 2 && !yrb::k2_supported(ix->dtype, ix->dim, k))
+        return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage and k <= %d", YRB_FUSED_K_MAX);
     if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
         return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
     if (path == 2) {
@@ -377,7 +426,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         int rc = prof_pair(ix, &ea, &eb);
         if (rc) return rc;
         rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
-                            ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, ix->sm_count, st,
+                            mask_q_stride, ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, ix->sm_count, st,
                             &launches, g_err, ea, eb);
         ix->launches += launches;
         return rc;
@@ -392,7 +441,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             int rc = prof_mark(ix, st);
             if (rc) return rc;
             CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
-                              ix->metric, mask, k, pk, ix->d_ticket, o, &fused, ix->sm_count, st));
+                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, k, pk, ix->d_ticket, o, &fused, ix->sm_count, st));
             if ((rc = prof_mark(ix, st))) return rc;
             ix->launches++;
             if (!fused) {
@@ -420,7 +469,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
     }
     for (int j = 0; j < nq; ++j) {
         CK(yrb::launch_scores(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
-                              ix->metric, mask, ix->d_rowkeys, ix->sm_count, st));
+                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, ix->d_rowkeys, ix->sm_count, st));
         CK(yrb::launch_select(ix->d_rowkeys, ix->rows, k, out_keys + (size_t)j * k, ix->d_select, ix->sm_count, st));
         ix->launches += 15;
     }
@@ -532,6 +581,9 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_DEV(ix->d_prog);
     FREE_DEV(ix->d_pass);
     FREE_DEV(ix->d_ticket);
+    FREE_DEV(ix->d_progs);
+    FREE_HOST(ix->h_progs);
+    FREE_DEV(ix->d_qmasks);
     FREE_HOST(ix->h_prog);
     FREE_HOST(ix->h_stage);
     for (auto& kv : ix->cols) {
@@ -753,8 +805,9 @@ int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64
     return YRB_OK;
 }
 
-int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w, const uint32_t* mask,
-                     int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+static int search_host(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w,
+                       const yrb_where* const* per_query, const uint32_t* mask, int64_t* out_ids, float* out_scores,
+                       int32_t* out_counts) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (nq < 1 || !queries) return fail(YRB_ERR_INVALID, "need at least one query");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
@@ -799,8 +852,15 @@ int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const y
         dev_extra = d_user;
     }
     const uint32_t* m = nullptr;
-    rc = resolve_mask(ix, w, dev_extra, &m, st, false);
-    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, ix->d_keys, ix->d_ids, ix->d_scores, ix->d_counts, st);
+    int64_t m_stride = 0;
+    if (per_query) {
+        // one filter per query (text2sql-style batches): every distinct program is evaluated once into
+        // its row of the [nq, words] mask matrix
+        rc = resolve_masks_multi(ix, per_query, nq, dev_extra, &m, &m_stride, st);
+    } else {
+        rc = resolve_mask(ix, w, dev_extra, &m, st, false);
+    }
+    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, m_stride, ix->d_keys, ix->d_ids, ix->d_scores, ix->d_counts, st);
     if (!rc) {
         cudaError_t e = cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -824,6 +884,17 @@ int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const y
     return YRB_OK;
 }
 
+int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w, const uint32_t* mask,
+                     int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+    return search_host(ix, queries, nq, k, w, nullptr, mask, out_ids, out_scores, out_counts);
+}
+
+int yrb_index_search_multi(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* const* wheres,
+                           int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+    if (!wheres) return fail(YRB_ERR_INVALID, "wheres is NULL (use yrb_index_search for a shared filter)");
+    return search_host(ix, queries, nq, k, nullptr, wheres, nullptr, out_ids, out_scores, out_counts);
+}
+
 int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k, const uint32_t* dev_mask,
                             uint64_t* dev_out_keys, void* stream) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
@@ -841,7 +912,7 @@ int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int
     if ((rc = ensure_scratch(ix, nq, k))) return rc;
     const uint32_t* m = nullptr;
     if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
-    return scan_select(ix, dev_queries, nq, k, m, dev_out_keys, nullptr, nullptr, nullptr, st);
+    return scan_select(ix, dev_queries, nq, k, m, 0, dev_out_keys, nullptr, nullptr, nullptr, st);
 }
 
 int yrb_index_search_device_ids(yrb_index* ix, const float* dev_queries, int nq, int k, const uint32_t* dev_mask,
@@ -858,7 +929,7 @@ int yrb_index_search_device_ids(yrb_index* ix, const float* dev_queries, int nq,
     if ((rc = ensure_scratch(ix, nq, k))) return rc;
     const uint32_t* m = nullptr;
     if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
-    return scan_select(ix, dev_queries, nq, k, m, ix->d_keys, dev_out_ids, dev_out_scores, dev_out_counts, st);
+    return scan_select(ix, dev_queries, nq, k, m, 0, ix->d_keys, dev_out_ids, dev_out_scores, dev_out_counts, st);
 }
 
 int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int nq, int k, const int64_t* dev_row_base,

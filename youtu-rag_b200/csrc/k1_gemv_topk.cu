@@ -25,7 +25,6 @@ constexpr int K1_THREADS = 512;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_R = 4;   // rows per batch
 constexpr int K1_CU = 4;  // chunks per unrolled step
-constexpr int K1_CHUNK = 64;  // rows per dynamically scheduled work item (= one 64-bit mask group)
 
 // CTAs of the scan.  YRB_K1_RESERVE_SMS leaves that many SMs free so that kernels of another stream
 // (the NCCL exchange of the previous search) can run beside the persistent scan.

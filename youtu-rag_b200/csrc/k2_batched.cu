@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                  int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                  float* __restrict__ tops, int m_tops, const unsigned char* __restrict__ rows_base, int row_bytes,
-                 int prefetch) {
+                 int prefetch, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
+                 int64_t mask_q_stride) {
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
     constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
@@ -329,6 +330,11 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
         if (!active) thr = INFINITY;
         float t0 = -INFINITY, t1 = -INFINITY;
         const bool sample_only = tops != nullptr;  // phase A: publish the best scores, append nothing
+        // euclidean: score = 1 - ||q||^2 - ||x||^2 + 2 q.x (chroma_store.py:132-135 on the l2 space)
+        const bool l2 = q_sqnorm != nullptr;
+        const float l2_bias = (l2 && active) ? 1.f - q_sqnorm[qi] : 0.f;
+        // filter bitmask: shared by all queries (stride 0) or one per query (text2sql-style batches)
+        const uint32_t* qmask = mask ? mask + (active ? (int64_t)qi * mask_q_stride : 0) : nullptr;
         int buf = 0;
         uint32_t bph = 0;
         for (int t = first; t < tile_end; t += step) {
@@ -370,8 +376,19 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                 const int64_t r0 = row0 + c * 32;
                 uint32_t mw = 0u;
                 if (r0 < n_rows) {
-                    mw = mask ? mask[r0 >> 5] : 0xffffffffu;
+                    mw = qmask ? qmask[r0 >> 5] : 0xffffffffu;
                     if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
+                    if (l2) {
+                        const float4* xn = reinterpret_cast<const float4*>(row_sqnorm + r0);  // r0 is 32-aligned
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 n4 = xn[j4];   // padded: sqnorm is allocated in multiples of 256 rows
+                            v[4 * j4 + 0] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 0]), l2_bias - n4.x));
+                            v[4 * j4 + 1] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 1]), l2_bias - n4.y));
+                            v[4 * j4 + 2] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 2]), l2_bias - n4.z));
+                            v[4 * j4 + 3] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 3]), l2_bias - n4.w));
+                        }
+                    }
                 }
                 if (sample_only) {
 #pragma unroll
@@ -499,7 +516,8 @@ template <int QB>
 static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows,
                                int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
                                const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const void* rows_base,
-                               int row_bytes, cudaStream_t st) {
+                               int row_bytes, const float* q_sqnorm, const float* row_sqnorm, int64_t mask_q_stride,
+                               cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -519,7 +537,7 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     static int pf = -1;
     if (pf < 0) pf = getenv("YRB_K2_PREFETCH") ? atoi(getenv("YRB_K2_PREFETCH")) : 1;
     return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
-                              reinterpret_cast<const unsigned char*>(rows_base), row_bytes, pf);
+                              reinterpret_cast<const unsigned char*>(rows_base), row_bytes, pf, q_sqnorm, row_sqnorm, mask_q_stride);
 }
 
 // cluster size for the query multicast: 2 always packs the 148 SMs (74 TPCs); override with YRB_K2_CLUSTER
@@ -535,15 +553,12 @@ static int k2_cluster(int grid) {
 }
 
 int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
-              int k, const uint32_t* mask, int metric, const float* q_sqnorm, const float* row_sqnorm,
-              uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
+              int k, const uint32_t* mask_all, int64_t mask_q_stride, int metric, const float* q_sqnorm,
+              const float* row_sqnorm, uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
               int* launches, std::string& err,
               cudaEvent_t ev_start, cudaEvent_t ev_stop) {
-    (void)capacity; (void)dim; (void)q_sqnorm; (void)row_sqnorm;
-    if (metric == YRB_METRIC_L2) {
-        err = "K2 handles cosine / dot; euclidean goes through K1";
-        return YRB_ERR_UNSUPPORTED;
-    }
+    (void)capacity; (void)dim;
+    const float* xn = metric == YRB_METRIC_L2 ? row_sqnorm : nullptr;
     if (!s->encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -579,6 +594,8 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         int grid = tiles < sm_count ? tiles : sm_count;
         const int cluster = k2_cluster(sm_count);
         grid = (grid + cluster - 1) / cluster * cluster;
+        const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
+        const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
         CUtensorMap mq;
         if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld,
                       QB * k2::BLOCK_Q / cluster, err))
@@ -593,10 +610,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (sampled) {
             if (QB == 2)
                 K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, st));
+                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, qn, xn, mask_q_stride, st));
             else
                 K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, st));
+                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, qn, xn, mask_q_stride, st));
             k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
             K2CK(cudaGetLastError());
             *launches += 2;
@@ -607,10 +624,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
         if (QB == 2)
             K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, rows, ld * 2, st));
+                                s->cand_cnt, nullptr, 0, rows, ld * 2, qn, xn, mask_q_stride, st));
         else
             K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, rows, ld * 2, st));
+                                s->cand_cnt, nullptr, 0, rows, ld * 2, qn, xn, mask_q_stride, st));
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
         const int gridB = grid;
         K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,

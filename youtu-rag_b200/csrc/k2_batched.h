@@ -15,7 +15,8 @@ int k2_parts(int sm_count);      // sorted k-lists K2 leaves per query before K3
 bool k2_supported(int dtype, int dim, int k);
 // q: prepared bf16 queries [nq, ld].  Writes nq*k keys (descending) to out_keys.  Returns YRB_* code.
 int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,
-              int k, const uint32_t* mask, int metric, const float* q_sqnorm, const float* row_sqnorm,
+              int k, const uint32_t* mask, int64_t mask_q_stride /*words between queries' masks, 0 = shared*/, int metric,
+              const float* q_sqnorm, const float* row_sqnorm,
               uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st, int* launches, std::string& err,
               cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);  // recorded around the main GEMM launch
 

@@ -31,7 +31,7 @@ EXPORTS = (
     "yrb_abi_version", "yrb_last_error", "yrb_device_count", "yrb_index_create", "yrb_index_destroy",
     "yrb_index_reserve", "yrb_index_count", "yrb_index_info", "yrb_index_append_host_f32",
     "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_set_live", "yrb_index_clear",
-    "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_device",
+    "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
     "yrb_index_profile_read",
@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
     L.yrb_index_column_write.argtypes = [vp, i32, i32, i64, i64, vp, vp]
     L.yrb_index_where.argtypes = [vp, C.POINTER(Where), vp, C.POINTER(i64)]
     L.yrb_index_search.argtypes = [vp, vp, i32, i32, C.POINTER(Where), vp, vp, vp, vp]
+    L.yrb_index_search_multi.argtypes = [vp, vp, i32, i32, C.POINTER(C.POINTER(Where)), vp, vp, vp]
     L.yrb_index_search_device.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.yrb_index_search_device_ids.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
@@ -140,7 +141,10 @@ class Index:
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:
-            lib().yrb_index_destroy(self._h)
+            try:
+                _lib.yrb_index_destroy(self._h)
+            except Exception:  # noqa: BLE001 - interpreter shutdown: module globals may already be gone
+                pass
             self._h = C.c_void_p()
 
     __del__ = close
@@ -205,8 +209,9 @@ class Index:
 
     # ------------------------------------------------------------ search
     def search(self, queries: np.ndarray, k: int, where: CompiledWhere | None = None,
-               mask: np.ndarray | None = None):
-        """Host buffers in / out.  Returns (ids int64[nq,k] (-1 pad), scores f32[nq,k], counts int32[nq])."""
+               mask: np.ndarray | None = None, wheres: list | None = None):
+        """Host buffers in / out.  Returns (ids int64[nq,k] (-1 pad), scores f32[nq,k], counts int32[nq]).
+        `where`: one compiled filter shared by all queries; `wheres`: one (or None) per query."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -216,6 +221,15 @@ class Index:
         ids = np.empty((nq, k), dtype=np.int64)
         scores = np.empty((nq, k), dtype=np.float32)
         counts = np.empty(nq, dtype=np.int32)
+        if wheres is not None:
+            if where is not None or mask is not None:
+                raise ValueError("pass either a shared filter (where/mask) or per-query filters (wheres)")
+            if len(wheres) != nq:
+                raise ValueError(f"expected {nq} per-query filters, got {len(wheres)}")
+            arr = (C.POINTER(Where) * nq)(*[C.pointer(w.struct) if w is not None else C.POINTER(Where)() for w in wheres])
+            _ck(lib().yrb_index_search_multi(self._h, q.ctypes.data, nq, k, arr, ids.ctypes.data, scores.ctypes.data,
+                                             counts.ctypes.data))
+            return ids, scores, counts
         mptr = None
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint32)

@@ -139,9 +139,12 @@ class B200VectorStore(BaseVectorStore):
         return out[0]
 
     async def search_batch(self, query_embeddings, top_k: int = 5,
-                           filters: dict[str, Any] | None = None) -> list[list[tuple[Chunk, float]]]:
+                           filters: dict[str, Any] | list[dict[str, Any] | None] | None = None
+                           ) -> list[list[tuple[Chunk, float]]]:
         """Q queries in one device pass (the batched entry point VectorRetriever.batch_retrieve uses;
-        the reference loops single searches, base_retriever.py:95-99)."""
+        the reference loops single searches, base_retriever.py:95-99).  `filters` is one filter for all
+        queries or a list with one filter (or None) per query — the shape of the text2sql value-linking
+        loop (unified_schemalink_valuelink.py:289-303: same vector, one metadata filter per column)."""
         q = np.asarray(query_embeddings, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -149,14 +152,28 @@ class B200VectorStore(BaseVectorStore):
             raise ValueError(f"Expected n_results to be a positive integer, got {top_k}")
         if not np.isfinite(q).all():
             raise ValueError("Query embedding contains NaN or infinite values")
+        per_query = isinstance(filters, (list, tuple))
+        if per_query and len(filters) != q.shape[0]:
+            raise ValueError(f"expected {q.shape[0]} filters (one per query), got {len(filters)}")
         if self._index is None or self._index.counts()[1] == 0:
-            compile_where(normalize_filters(filters), self._meta)  # still validate like Chroma would
+            for f in (filters if per_query else [filters]):  # still validate like Chroma would
+                compile_where(normalize_filters(f), self._meta)
             return [[] for _ in range(q.shape[0])]
         if q.shape[1] != self._index.dim:
             raise ValueError(
                 f"Embedding dimension {q.shape[1]} does not match collection dimensionality {self._index.dim}")
-        compiled = self._compile(filters)
-        ids, scores, counts = self._index.search(q, int(top_k), where=compiled)
+        if per_query:
+            cache: dict[str, Any] = {}
+            compiled_list = []
+            for f in filters:
+                key = repr(f)
+                if key not in cache:
+                    cache[key] = self._compile(f)
+                compiled_list.append(cache[key])  # identical filters share one program (evaluated once)
+            ids, scores, counts = self._index.search(q, int(top_k), wheres=compiled_list)
+        else:
+            compiled = self._compile(filters)
+            ids, scores, counts = self._index.search(q, int(top_k), where=compiled)
         results = []
         for j in range(q.shape[0]):
             n = int(counts[j])
