@@ -78,6 +78,12 @@ YRB_API int yrb_index_append_host_f32(yrb_index* ix, const float* rows, int64_t 
 YRB_API int yrb_index_append_device_f32(yrb_index* ix, const float* dev_rows, int64_t n, void* stream);
 /* stored rows decoded back to fp32 (Chunk.embedding of get_by_id, chroma_store.py:236-245). */
 YRB_API int yrb_index_read_rows(yrb_index* ix, const int64_t* row_ids, int64_t n, float* out_rows);
+/* Persistence (Chroma's on-disk segments, chroma_store.py:41-44): rows exactly as stored
+ * (storage dtype, ld elements per row — see yrb_index_info) plus their squared norms, so that a reload
+ * is bit-identical without re-normalising.  read_raw copies rows [row_begin, row_begin+n) to the host;
+ * append_raw appends n such rows. */
+YRB_API int yrb_index_read_raw(yrb_index* ix, int64_t row_begin, int64_t n, void* out_rows, float* out_sqnorm);
+YRB_API int yrb_index_append_raw(yrb_index* ix, const void* rows, const float* sqnorm, int64_t n);
 /* collection.delete (chroma_store.py:150-160): tombstone / revive rows; tombstoned rows are
  * invisible to search. */
 YRB_API int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int live);

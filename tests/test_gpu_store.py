@@ -117,3 +117,31 @@ def test_retriever_over_b200_store_matches_reference_retriever():
         for got, want in [(single, rec["single"])] + list(zip(batch, rec["batch"])):
             assert [x.rank for x in got] == [w["rank"] for w in want]
             compare_with_golden([(x.chunk, x.score) for x in got], want, tol=1e-5)
+
+
+def test_persistence_roundtrip_is_bit_identical(tmp_path):
+    """f1: add → delete → reopen from disk → same ids, same scores (bitwise), same metadata; then keep writing."""
+    cfg = VectorStoreConfig(collection_name="p", persist_directory=str(tmp_path), distance_metric="cosine",
+                            index_params={"persist": True})
+    a = B200VectorStore(cfg)
+    ch = golden_chunks()
+    run(a.add_chunks(ch[:40]))
+    run(a.add_chunks(ch[40:]))
+    run(a.delete_by_document_id("doc2"))
+    run(a.delete(["doc0_chunk_0"]))
+    want = [run(a.search(q, 7, {"source": {"$in": ["file0.pdf", "file1.pdf"]}})) for q in GOLDEN["queries"]]
+    n = run(a.count())
+    a.close()
+    b = B200VectorStore(cfg)
+    assert run(b.count()) == n and run(b.get_by_id("doc0_chunk_0")) is None
+    for q, w in zip(GOLDEN["queries"], want):
+        got = run(b.search(q, 7, {"source": {"$in": ["file0.pdf", "file1.pdf"]}}))
+        assert [(c.id, s, c.metadata, c.content) for c, s in got] == [(c.id, s, c.metadata, c.content) for c, s in w]
+    run(b.add_chunks(ch[:3]))                 # doc0_chunk_0 was deleted → can be added again; the other two exist
+    assert run(b.count()) == n + 1
+    b.close()
+    c = B200VectorStore(cfg)
+    assert run(c.count()) == n + 1 and run(c.get_by_id("doc0_chunk_0")) is not None
+    run(c.clear())
+    assert not (tmp_path / "p.b200").exists()
+    assert run(B200VectorStore(cfg).count()) == 0

@@ -705,6 +705,41 @@ int yrb_index_read_rows(yrb_index* ix, const int64_t* row_ids, int64_t n, float*
     return YRB_OK;
 }
 
+int yrb_index_read_raw(yrb_index* ix, int64_t row_begin, int64_t n, void* out_rows, float* out_sqnorm) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || row_begin < 0 || row_begin + n > ix->rows) return fail(YRB_ERR_INVALID, "row range out of bounds");
+    if (n == 0) return YRB_OK;
+    if (!out_rows || !out_sqnorm) return fail(YRB_ERR_INVALID, "output buffers are NULL");
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    const size_t rb = (size_t)ix->ld * yrb::elem_size(ix->dtype);
+    CK(cudaMemcpyAsync(out_rows, reinterpret_cast<char*>(ix->d_rows) + (size_t)row_begin * rb, (size_t)n * rb,
+                       cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaMemcpyAsync(out_sqnorm, ix->d_sqnorm + row_begin, (size_t)n * 4, cudaMemcpyDeviceToHost, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    return YRB_OK;
+}
+
+int yrb_index_append_raw(yrb_index* ix, const void* rows, const float* sqnorm, int64_t n) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || (n > 0 && (!rows || !sqnorm))) return fail(YRB_ERR_INVALID, "bad arguments");
+    if (n == 0) return YRB_OK;
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if (ix->rows + n > 0xfffffffell) return fail(YRB_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
+    if ((rc = ensure_capacity(ix, ix->rows + n))) return rc;
+    const size_t rb = (size_t)ix->ld * yrb::elem_size(ix->dtype);
+    CK(cudaMemcpyAsync(reinterpret_cast<char*>(ix->d_rows) + (size_t)ix->rows * rb, rows, (size_t)n * rb,
+                       cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaMemcpyAsync(ix->d_sqnorm + ix->rows, sqnorm, (size_t)n * 4, cudaMemcpyHostToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    if ((rc = mark_appended(ix, ix->rows, n))) return rc;
+    ix->rows += n;
+    return YRB_OK;
+}
+
 int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int live) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && !row_ids)) return fail(YRB_ERR_INVALID, "bad arguments");

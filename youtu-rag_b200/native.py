@@ -30,7 +30,7 @@ WHERE_MAX_LEAVES, WHERE_MAX_OPERANDS, WHERE_MAX_TOKENS = 64, 256, 160
 EXPORTS = (
     "yrb_abi_version", "yrb_last_error", "yrb_device_count", "yrb_index_create", "yrb_index_destroy",
     "yrb_index_reserve", "yrb_index_count", "yrb_index_info", "yrb_index_append_host_f32",
-    "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_set_live", "yrb_index_clear",
+    "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_read_raw", "yrb_index_append_raw", "yrb_index_set_live", "yrb_index_clear",
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
     L.yrb_index_append_host_f32.argtypes = [vp, vp, i64]
     L.yrb_index_append_device_f32.argtypes = [vp, vp, i64, vp]
     L.yrb_index_read_rows.argtypes = [vp, vp, i64, vp]
+    L.yrb_index_read_raw.argtypes = [vp, i64, i64, vp, vp]
+    L.yrb_index_append_raw.argtypes = [vp, vp, vp, i64]
     L.yrb_index_set_live.argtypes = [vp, vp, i64, i32]
     L.yrb_index_clear.argtypes = [vp]
     L.yrb_index_column_write.argtypes = [vp, i32, i32, i64, i64, vp, vp]
@@ -183,6 +185,22 @@ class Index:
         out = np.empty((ids.shape[0], self.dim), dtype=np.float32)
         _ck(lib().yrb_index_read_rows(self._h, ids.ctypes.data, ids.shape[0], out.ctypes.data))
         return out
+
+    def read_raw(self, row_begin: int, n: int) -> tuple[np.ndarray, np.ndarray]:
+        """Rows exactly as stored: (uint16 [n, ld] bf16 bits or float32 [n, ld], float32 [n] squared norms)."""
+        ld = self.info()["ld"]
+        rows = np.empty((n, ld), dtype=np.uint16 if self.dtype == "bf16" else np.float32)
+        sq = np.empty(n, dtype=np.float32)
+        _ck(lib().yrb_index_read_raw(self._h, row_begin, n, rows.ctypes.data, sq.ctypes.data))
+        return rows, sq
+
+    def append_raw(self, rows: np.ndarray, sqnorm: np.ndarray) -> None:
+        ld = self.info()["ld"]
+        rows = np.ascontiguousarray(rows, dtype=np.uint16 if self.dtype == "bf16" else np.float32)
+        sqnorm = np.ascontiguousarray(sqnorm, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != ld or sqnorm.shape[0] != rows.shape[0]:
+            raise ValueError(f"expected raw rows [n, {ld}] and n squared norms")
+        _ck(lib().yrb_index_append_raw(self._h, rows.ctypes.data, sqnorm.ctypes.data, rows.shape[0]))
 
     def set_live(self, row_ids, live: bool) -> None:
         ids = np.ascontiguousarray(row_ids, dtype=np.int64)

@@ -28,6 +28,7 @@ from . import native
 from .base import BaseVectorStore, Chunk
 from .config import VectorStoreConfig
 from .metadata import MetadataTable
+from .persist import CollectionDir
 from .where import compile_where, normalize_filters
 
 logger = logging.getLogger(__name__)
@@ -57,6 +58,12 @@ class B200VectorStore(BaseVectorStore):
         self._metadatas: list[dict[str, Any] | None] = []
         self._row_of: dict[str, int] = {}
         self._meta = MetadataTable()
+        self._deleted: set[int] = set()   # tombstoned row numbers (rows are stable across reloads)
+        # persistence is opt-in (index_params.persist): the reference's Chroma client always persists
+        # (chroma_store.py:41-44); here an in-memory collection is the default so tests leave no files
+        self._dir = CollectionDir(config.persist_directory, config.collection_name) if p.get("persist") else None
+        if self._dir is not None and self._dir.exists():
+            self._load()
         logger.info("Initialized B200 vector store (collection %s, metric %s, storage %s, device %d)",
                     config.collection_name, metric, self._dtype, self._device)
 
@@ -92,6 +99,30 @@ class B200VectorStore(BaseVectorStore):
             return []
         bits = np.unpackbits(words.view(np.uint8), bitorder="little")[: self._index.rows]
         return np.flatnonzero(bits).tolist()
+
+    def _load(self) -> None:
+        m = self._dir.manifest()
+        if (m["metric"], m["dtype"]) != (self._metric, self._dtype):
+            raise ValueError(f"collection on disk is {m['metric']}/{m['dtype']}, config asks {self._metric}/{self._dtype}")
+        index = self._ensure_index(m["dim"])
+        for rows, sqnorm, recs in self._dir.segments():
+            base = index.rows
+            index.append_raw(rows, sqnorm)
+            for i, r in enumerate(recs):
+                self._row_of[r["id"]] = base + i
+            self._ids.extend(r["id"] for r in recs)
+            self._documents.extend(r["document"] for r in recs)
+            self._metadatas.extend(r["metadata"] for r in recs)
+            self._meta.append([r["metadata"] for r in recs])
+        gone = [r for r in self._dir.deleted() if 0 <= r < index.rows]
+        if gone:
+            index.set_live(gone, False)
+            for r in gone:
+                if self._row_of.get(self._ids[r]) == r:   # not re-added by a later segment
+                    del self._row_of[self._ids[r]]
+                self._ids[r] = self._documents[r] = self._metadatas[r] = None
+            self._deleted.update(gone)
+        logger.info("Loaded %d chunks (%d deleted) from %s", len(self._row_of), len(gone), self._dir.path)
 
     # ------------------------------------------------------------------ BaseVectorStore
     async def add_chunks(self, chunks: list[Chunk]) -> None:
@@ -131,6 +162,11 @@ class B200VectorStore(BaseVectorStore):
         self._documents.extend(c.content for c in fresh)
         self._metadatas.extend(metas)
         self._meta.append(metas)
+        if self._dir is not None:
+            if not self._dir.exists():
+                self._dir.create(index.dim, self._metric, self._dtype, index.info()["ld"])
+            raw, sq = index.read_raw(base, len(fresh))   # exactly what the device holds
+            self._dir.append_segment(raw, sq, [c.id for c in fresh], [c.content for c in fresh], metas)
         logger.info("Added %d chunks to B200 index", len(fresh))
 
     async def search(self, query_embedding: list[float], top_k: int = 5,
@@ -190,6 +226,9 @@ class B200VectorStore(BaseVectorStore):
             self._index.set_live(rows, False)
             for r in rows:
                 self._ids[r] = self._documents[r] = self._metadatas[r] = None
+            if self._dir is not None:
+                self._deleted.update(rows)
+                self._dir.write_deleted(list(self._deleted))
         logger.info("Deleted %d chunks from B200 index", len(rows))
 
     async def delete_by_document_id(self, document_id: str) -> int:
@@ -229,6 +268,9 @@ class B200VectorStore(BaseVectorStore):
             self._index.clear()
         self._ids, self._documents, self._metadatas, self._row_of = [], [], [], {}
         self._meta.clear()
+        self._deleted.clear()
+        if self._dir is not None:
+            self._dir.remove()
         logger.info("Cleared B200 collection: %s", self.config.collection_name)
 
     # ------------------------------------------------------------------ extras
