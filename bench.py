@@ -243,15 +243,7 @@ def run_b200(args):
     searcher = ShardedSearcher(index, bounds)
     st = searcher.stream  # every kernel of a step is launched on this stream
 
-    # multi-GPU steps are replayed from CUDA graphs (scan graph + exchange graph per result slot): the host
-    # cost of ~6 launches + an NCCL enqueue per step would otherwise bound small shards
-    use_graphs = world > 1 and not args.no_graphs
-    if use_graphs:
-        searcher.capture(nq, k, dev_mask)
-
     def step_device(i):
-        if use_graphs:
-            return searcher.replay(dq[i % N_QUERY_SETS])
         return searcher.search_device(dq[i % N_QUERY_SETS], k, dev_mask)
 
     def barrier():
@@ -263,7 +255,7 @@ def run_b200(args):
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    index.profile(not use_graphs)   # event records cannot be read back from a replayed graph
+    index.profile(True)
     index.profile_read()
     l0 = index.launches()
     sampler = ClockSampler(local)
@@ -282,22 +274,6 @@ def run_b200(args):
     launches = index.launches() - l0 + (args.steps if world > 1 else 0)  # + the K3 global merge per step
     kern_ms, kern_n = index.profile_read()
     index.profile(False)
-    kernel_timing = "inside the timed region"
-    if use_graphs:
-        # same steps once more without graphs, only to time the dominant kernel with CUDA events
-        barrier()
-        index.profile(True)
-        index.profile_read()
-        n_pass = min(args.steps, 100)
-        l1 = index.launches()
-        for i in range(n_pass):
-            searcher.search_device(dq[i % N_QUERY_SETS], k, dev_mask)
-        barrier()
-        kern_ms, kern_n = index.profile_read()
-        index.profile(False)
-        kernel_timing = "separate un-graphed pass of the same steps (event records are not readable from graph replays)"
-        # a replayed step launches the same kernels as an un-graphed one (+ the K3 global merge)
-        launches = int(((index.launches() - l1) / n_pass + 1) * args.steps)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -348,7 +324,7 @@ def run_b200(args):
     if tp.exists():
         traffic = json.loads(tp.read_text()).get(args.workload)
     kern_avg_ms = kern_ms / max(1, kern_n)
-    launches_per_step = kern_n / (min(args.steps, 100) if use_graphs else args.steps)
+    launches_per_step = kern_n / args.steps
     if nq < 8 or args.path == 1:
         # K1: one launch scans the shard once for one query
         algo_bytes = frac_rows * n_local * dim * 2 + (n_local / 8 if sel else 0) + dim * 2 + 148 * k * 8
@@ -393,9 +369,6 @@ def run_b200(args):
                     "steps": e2e_steps, "api": "yrb_index_search (C ABI, host buffers)" if world == 1 and dev_mask is None
                     else "ShardedSearcher.search (host buffers)"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "step_issue": ("cuda-graph replay (scan graph + exchange graph), exchange of step i overlaps scan of step i+1"
-                           if use_graphs else "direct launches on one stream"),
-            "kernel_timing": kernel_timing,
         }
         print(json.dumps(line))
     if world > 1:
@@ -411,7 +384,6 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", type=int, default=0, help="force kernel family: 1 K1, 2 K2, 3 K6")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-graphs", action="store_true", help="multi-GPU: issue steps as direct launches, not graph replays")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

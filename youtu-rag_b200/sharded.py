@@ -95,58 +95,6 @@ class ShardedSearcher:
             b["merged"].record(self.comm_stream)
         return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
 
-    # ------------------------------------------------------------------ CUDA-graph replay (world > 1)
-    def capture(self, nq: int, k: int, dev_mask: torch.Tensor | None = None):
-        """Capture the step for a fixed (nq, k, mask) into CUDA graphs: per result slot one graph for the
-        scan (on `stream`) and one for the exchange + merge (on `comm_stream`).  A step then costs two graph
-        launches and two event operations on the host instead of ~6 launches plus the NCCL enqueue, which
-        is what bounds small shards.  Returns the static query tensor [nq, dim] to copy queries into."""
-        assert self.world > 1, "a single-GPU search is already one launch"
-        dim = self.index.dim
-        static_q = torch.zeros(nq, dim, dtype=torch.float32, device=self.device)
-        slots = self._buffers(nq, k)
-        mptr = dev_mask.data_ptr() if dev_mask is not None else 0
-        self.index.profile(False)
-        # warm up outside capture (allocations, NCCL channel setup)
-        for _ in range(3):
-            self.search_device(static_q, k, dev_mask)
-        self.synchronize()
-        graphs = []
-        for b in slots:
-            g_scan, g_exch = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_scan, stream=self.stream):
-                self.index.search_device(static_q.data_ptr(), nq, k, mptr, b["local"].data_ptr(), self.stream.cuda_stream)
-            with torch.cuda.graph(g_exch, stream=self.comm_stream):
-                dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
-                native.merge_topk_device(self.index.device, b["gathered"].data_ptr(), self.world, nq, k,
-                                         self._base_dev.data_ptr(), b["ids"].data_ptr(), b["scores"].data_ptr(),
-                                         b["counts"].data_ptr(), self.comm_stream.cuda_stream)
-            graphs.append((g_scan, g_exch))
-        self._graphs = {"nq": nq, "k": k, "q": static_q, "graphs": graphs, "mask": dev_mask}
-        self.synchronize()
-        return static_q
-
-    def replay(self, dev_queries: torch.Tensor | None = None):
-        """One captured step.  dev_queries (optional) is copied into the static query tensor first."""
-        G = self._graphs
-        nq, k = G["nq"], G["k"]
-        slots = self._buffers(nq, k)
-        i = self._turn % self.depth
-        b = slots[i]
-        self._turn += 1
-        g_scan, g_exch = G["graphs"][i]
-        with torch.cuda.stream(self.stream):
-            if dev_queries is not None:
-                G["q"].copy_(dev_queries, non_blocking=True)
-            self.stream.wait_event(b["merged"])
-            g_scan.replay()
-            b["scanned"].record(self.stream)
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(b["scanned"])
-            g_exch.replay()
-            b["merged"].record(self.comm_stream)
-        return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
-
     def synchronize(self) -> None:
         self.stream.synchronize()
         self.comm_stream.synchronize()
