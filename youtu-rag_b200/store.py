@@ -169,6 +169,26 @@ class B200VectorStore(BaseVectorStore):
             self._dir.append_segment(raw, sq, [c.id for c in fresh], [c.content for c in fresh], metas)
         logger.info("Added %d chunks to B200 index", len(fresh))
 
+    async def upsert_chunks(self, chunks: list[Chunk]) -> None:
+        """collection.upsert (memory_store.py:278-283): an existing id is replaced — its old row is
+        tombstoned and the new embedding / text / metadata appended."""
+        if not chunks:
+            return
+        last = {c.id: c for c in chunks}            # within one call the last occurrence of an id wins
+        await self.delete([cid for cid in last if cid in self._row_of])
+        await self.add_chunks(list(last.values()))
+
+    async def get_where(self, where: dict[str, Any] | None, include_embeddings: bool = False) -> list[Chunk]:
+        """collection.get(where=…) (memory_store.py:442-451): every live chunk passing the filter, in row order."""
+        if self._index is None:
+            return []
+        if where is None:
+            rows = sorted(self._row_of.values())
+        else:
+            rows = self._rows_matching(where)
+        embs = self._index.read_rows(rows).tolist() if (include_embeddings and rows) else [None] * len(rows)
+        return [self._make_chunk(r, e) for r, e in zip(rows, embs)]
+
     async def search(self, query_embedding: list[float], top_k: int = 5,
                      filters: dict[str, Any] | None = None) -> list[tuple[Chunk, float]]:
         out = await self.search_batch([query_embedding], top_k=top_k, filters=filters)
