@@ -59,6 +59,7 @@ struct yrb_index {
     float* d_sqnorm = nullptr;
     uint32_t* d_live = nullptr;  // mask_words(capacity)
     uint32_t* d_mask = nullptr;  // filter scratch, same size
+    uint32_t* d_usermask = nullptr;  // device copy of a caller-supplied host bitmask, same size
     std::vector<uint32_t> h_live;
     std::map<int, Column> cols;
     cudaStream_t stream = nullptr;
@@ -138,6 +139,7 @@ int ensure_capacity(yrb_index* ix, int64_t want) {
     const size_t ow = (size_t)mask_words(ix->capacity) * 4, nw = (size_t)mask_words(cap) * 4;
     if ((rc = regrow(&ix->d_live, ix->capacity ? ow : 0, nw, true, ix->stream))) return rc;
     if ((rc = regrow(&ix->d_mask, 0, nw, true, ix->stream))) return rc;
+    if ((rc = regrow(&ix->d_usermask, 0, nw, true, ix->stream))) return rc;
     ix->h_live.resize(mask_words(cap), 0u);
     for (auto& kv : ix->cols) {
         Column& c = kv.second;
@@ -576,6 +578,7 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_DEV(ix->d_sqnorm);
     FREE_DEV(ix->d_live);
     FREE_DEV(ix->d_mask);
+    FREE_DEV(ix->d_usermask);
     FREE_DEV(ix->d_rowkeys);
     FREE_DEV(ix->d_select);
     FREE_DEV(ix->d_prog);
@@ -868,10 +871,9 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     CK(cudaMemcpyAsync(ix->d_qf32, ix->h_q, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, st));
     const size_t res_bytes = result_views(ix, nq, ke);
     const uint32_t* dev_extra = nullptr;
-    uint32_t* d_user = nullptr;
     if (mask) {
+        uint32_t* d_user = ix->d_usermask;
         const int64_t nw = (ix->rows + 31) / 32, nwp = mask_words(ix->rows);
-        CK(cudaMalloc(&d_user, (size_t)nwp * 4));
         cudaError_t e = cudaMemsetAsync(d_user, 0, (size_t)nwp * 4, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_user, mask, (size_t)nw * 4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess && (ix->rows & 31)) {
@@ -880,10 +882,7 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
             e = cudaMemcpyAsync(d_user + nw - 1, &last, 4, cudaMemcpyHostToDevice, st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         }
-        if (e != cudaSuccess) {
-            cudaFree(d_user);
-            return fail(YRB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
-        }
+        if (e != cudaSuccess) return fail(YRB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
         dev_extra = d_user;
     }
     const uint32_t* m = nullptr;
@@ -903,7 +902,6 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     } else {
         cudaStreamSynchronize(st);
     }
-    if (d_user) cudaFree(d_user);
     if (rc) return rc;
     const int64_t* h_ids = reinterpret_cast<const int64_t*>(ix->h_result);
     const float* h_scores = reinterpret_cast<const float*>(ix->h_result + (size_t)nq * ke * 8);

@@ -30,165 +30,12 @@
 #include "../../include/yrb200.h"
 #include "common.cuh"
 #include "k2_batched.h"
+#include "k2_common.cuh"
 #include "kernels.h"
 
 namespace yrb {
 
 namespace k2 {
-
-constexpr int BLOCK_Q = 128;   // MMA M: queries per query block
-constexpr int BLOCK_R = 128;   // MMA N: corpus rows per tile (256 measured slower: no accumulator double-buffering)
-constexpr int BLOCK_K = 64;    // bf16 elements per k-block = one 128-byte swizzle atom
-constexpr int UMMA_K = 16;
-constexpr int CAP = 256;       // candidate slots per (CTA, query)
-constexpr int MAX_Q = 256;     // queries per launch (2 query blocks)
-constexpr int QTILE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KiB: one query block x one k-block
-constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 32 KiB: one row tile x one k-block
-constexpr int MAX_TOPS = 2;
-
-__host__ __device__ constexpr int stages(int qb) { return (220 * 1024) / (qb * QTILE_BYTES + RTILE_BYTES); }
-// accumulator buffers in the 512 TMEM columns: QB=1 → 2 x 256, QB=2 → 1 x 512 (epilogue not overlapped)
-__host__ __device__ constexpr int acc_buffers(int qb) { return 512 / (qb * BLOCK_R) >= 2 ? 2 : 1; }
-__host__ __device__ constexpr int stage_bytes(int qb) { return qb * QTILE_BYTES + RTILE_BYTES; }
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (true) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each
-// destination CTA's barrier (same offset) receives the complete_tx
-__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                                  uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-        : "memory");
-}
-// contiguous bulk prefetch into L2 (whole rows: DRAM-page friendly, unlike the 128-byte column slabs of a box)
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// arrives on the barrier at the same offset in every CTA of `mask` once the MMAs issued so far complete
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
-        "%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (version 1 = Blackwell):
-// start address >> 4 | LBO(1) << 16 | SBO (8 rows x 128 B = 1024 B >> 4) << 32 | version << 46 | layout(2) << 61
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_R >> 3) << 17) |
-                           ((uint32_t)(BLOCK_Q >> 4) << 24);
-
-// ---------------------------------------------------------------- warp bitonic sort of 256 keys
-// element e = i*32 + lane, descending.
-__device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
-#pragma unroll
-    for (int size = 2; size <= 256; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32) {
-                const int ri = stride >> 5;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if ((i & ri) == 0) {
-                        const int e = i * 32 + lane;
-                        const bool desc = (e & size) == 0;
-                        uint64_t a = v[i], b = v[i | ri];
-                        const bool sw = desc ? (b > a) : (a > b);
-                        v[i] = sw ? b : a;
-                        v[i | ri] = sw ? a : b;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int e = i * 32 + lane;
-                    const bool desc = (e & size) == 0;
-                    const bool lower = (lane & stride) == 0;
-                    const uint64_t o = shfl_xor_u64(v[i], stride);
-                    const uint64_t mx = v[i] > o ? v[i] : o, mn = v[i] > o ? o : v[i];
-                    v[i] = (lower == desc) ? mx : mn;
-                }
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------- the kernel
 template <int QB>
@@ -440,14 +287,18 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
 // ---------------------------------------------------------------- thresholds from phase A
 // thr0[q] = k-th largest of the (n_cta * m) published best scores: every one is the score of a distinct
 // real row, so at least k rows score >= thr0[q] and thr0[q] <= the true k-th best.  Fewer than k → -inf.
+// cta_stride 1: every CTA published for every query; 2 (pair kernel): CTA 2i + (q >= 128) published for q.
 __global__ void __launch_bounds__(256) k2_threshold_kernel(const float* __restrict__ tops, int n_cta, int m, int k,
-                                                           float* __restrict__ thr0) {
+                                                           float* __restrict__ thr0, int cta_stride) {
     __shared__ float sv[512];
     const int q = blockIdx.x;
     const int n = n_cta * m;
     for (int i = threadIdx.x; i < 512; i += blockDim.x) {
         float v = -INFINITY;
-        if (i < n) v = tops[((int64_t)(i / m) * MAX_TOPS + (i % m)) * MAX_Q + q];
+        if (i < n) {
+            const int cta = (i / m) * cta_stride + (cta_stride == 2 && q >= BLOCK_Q ? 1 : 0);
+            v = tops[((int64_t)cta * MAX_TOPS + (i % m)) * MAX_Q + q];
+        }
         sv[i] = v;
     }
     block_bitonic_desc(sv, 512, [](float a, float b) { return a > b; });
@@ -540,6 +391,13 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
                               reinterpret_cast<const unsigned char*>(rows_base), row_bytes, pf, q_sqnorm, row_sqnorm, mask_q_stride);
 }
 
+// CTA-pair kernel for 129..256-query chunks (YRB_K2_PAIR=0 keeps the one-CTA kernel)
+static bool k2_use_pair() {
+    static int v = -1;
+    if (v < 0) v = getenv("YRB_K2_PAIR") ? atoi(getenv("YRB_K2_PAIR")) : 1;
+    return v != 0;
+}
+
 // cluster size for the query multicast: 2 always packs the 148 SMs (74 TPCs); override with YRB_K2_CLUSTER
 static int k2_cluster(int grid) {
     static int forced = -1;
@@ -590,12 +448,46 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
     for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
         const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
+        const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
+        const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
+        if (nqc > k2::BLOCK_Q && k2_use_pair()) {
+            // CTA pairs (cta_group::2): 256-row tiles, CTA r of a pair owns queries [128r, 128r+128)
+            const int tiles2 = (int)((n_rows + 255) / 256);
+            int n_pairs = sm_count / 2;
+            if (tiles2 < n_pairs) n_pairs = tiles2;
+            const int grid2 = 2 * n_pairs;
+            CUtensorMap mq2;
+            if (!make_map(s, &mq2, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld, k2::BLOCK_Q, err))
+                return YRB_ERR_CUDA;
+            K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)s->slots * k2::MAX_Q * 4, st));
+            const int m_tops2 = (2 * k + n_pairs - 1) / n_pairs <= 1 ? 1 : k2::MAX_TOPS;
+            const bool sampled2 = tiles2 > 2 * n_pairs && (int64_t)n_pairs * m_tops2 >= k;
+            const float* thr2 = nullptr;
+            if (sampled2) {
+                K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, 1, nqc, k, mask, mask_q_stride, nullptr, s->cand_keys,
+                                      s->cand_cnt, s->tops, m_tops2, qn, xn, st));
+                k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, n_pairs, m_tops2, k, s->thr0, 2);
+                K2CK(cudaGetLastError());
+                *launches += 2;
+                thr2 = s->thr0;
+            }
+            const int iters2 = (tiles2 + n_pairs - 1) / n_pairs;
+            if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
+            K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, iters2, nqc, k, mask, mask_q_stride, thr2, s->cand_keys,
+                                  s->cand_cnt, nullptr, 0, qn, xn, st));
+            if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
+            K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, grid2, 0,
+                                        k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st,
+                                        out_ids ? out_ids + (size_t)c0 * k : nullptr,
+                                        out_scores ? out_scores + (size_t)c0 * k : nullptr,
+                                        out_counts ? out_counts + c0 : nullptr));
+            *launches += 2;
+            continue;
+        }
         // grids are multiples of the cluster size; every CTA runs the same number of tiles
         int grid = tiles < sm_count ? tiles : sm_count;
         const int cluster = k2_cluster(sm_count);
         grid = (grid + cluster - 1) / cluster * cluster;
-        const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
-        const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
         CUtensorMap mq;
         if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld,
                       QB * k2::BLOCK_Q / cluster, err))
@@ -614,7 +506,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             else
                 K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
                                     s->cand_cnt, s->tops, m_tops, rows, ld * 2, qn, xn, mask_q_stride, st));
-            k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0);
+            k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0, 1);
             K2CK(cudaGetLastError());
             *launches += 2;
             thr = s->thr0;

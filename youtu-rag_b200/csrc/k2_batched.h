@@ -20,4 +20,12 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st, int* launches, std::string& err,
               cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);  // recorded around the main GEMM launch
 
+// pair kernel (k2_pair.cu)
+}  // namespace yrb
+#include <cuda.h>
+namespace yrb {
+cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks, int iters,
+                             int nq, int k, const uint32_t* mask, int64_t mask_q_stride, const float* thr, uint64_t* ck,
+                             int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm,
+                             cudaStream_t st);
 }  // namespace yrb

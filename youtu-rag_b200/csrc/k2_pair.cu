@@ -1,0 +1,287 @@
+// K2 (pair form) — the batched GEMM + fused top-k epilogue on CTA PAIRS: tcgen05.mma.cta_group::2,
+// M = 256 queries (128 per CTA) x N = 256 corpus rows (128 loaded by each CTA) x K = 16.
+//
+// Why pairs: the one-CTA kernel (k2_batched.cu) is bound by bytes entering each SM — every k-block it
+// ingests its 128 corpus rows (16 KiB, from HBM) AND the whole 256-query k-block (32 KiB, from L2), 48 KiB
+// per 2.1 M MACs, at a measured ~52 B/clk/SM.  In a pair each SM ingests only its half of the queries and
+// its half of the rows (32 KiB per 2.1 M MACs); the tensor cores read the other halves from the peer SM's
+// shared memory.  Used for 129..256-query chunks; smaller chunks stay on the one-CTA kernel.
+//
+// Protocol (CTA 0 of the pair = leader):
+//   * both CTAs' producers TMA their halves with the .cta_group::2 form, signalling the LEADER's full barrier
+//     (64 KiB of transactions per stage); each waits on its OWN empty barrier,
+//   * the leader's MMA thread issues the 2-SM MMAs; commits are multicast to both CTAs' empty / tmem-full
+//     barriers,
+//   * each CTA's 4 epilogue warps drain its 128 TMEM lanes (= its 128 queries) x 256 columns (= all 256 rows
+//     of the pair's tile) and arrive on the LEADER's tmem-empty barrier (count 8).
+// Epilogue, thresholds, candidate buffers and selection are those of k2_batched.cu.
+#include <cstdlib>
+
+#include "../../include/yrb200.h"
+#include "k2_batched.h"
+#include "k2_common.cuh"
+#include "kernels.h"
+
+namespace yrb {
+namespace k2 {
+
+constexpr int PAIR_N = 256;              // rows per pair tile (MMA N)
+constexpr int PAIR_STAGES = 6;           // 32 KiB per CTA per stage
+constexpr int PAIR_STAGE_BYTES = 2 * QTILE_BYTES;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-parity bit of a shared::cluster address → leader
+// kind::f16, D = F32, A = B = BF16, K-major, M = 256 (pair), N = 256
+constexpr uint32_t IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(PAIR_N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+    k2_gemm_topk_pair(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows,
+                      int kblocks, int iters, int nq, int k, const uint32_t* __restrict__ mask, int64_t mask_q_stride,
+                      const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
+                      float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm,
+                      const float* __restrict__ row_sqnorm) {
+    constexpr int S = PAIR_STAGES;
+    constexpr int ACC_COLS = PAIR_N;  // per buffer; two buffers = all 512 columns
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[2 * S + 4];
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+    const uint32_t smem0 = (smem_u32(smem) + 1023u) & ~1023u;
+    auto full_bar = [&](int s) { return smem_u32(&bars[s]); };
+    auto empty_bar = [&](int s) { return smem_u32(&bars[S + s]); };
+    auto tfull_bar = [&](int b) { return smem_u32(&bars[2 * S + b]); };
+    auto tempty_bar = [&](int b) { return smem_u32(&bars[2 * S + 2 + b]); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);   // leader: its producer's arrive.expect_tx; peer's copy is unused
+            mbar_init(empty_bar(s), 1);  // one multicast commit per round
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 8);  // 4 epilogue warps of each CTA arrive at the LEADER's barrier
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {  // the same warp id in both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int n_pairs = (int)gridDim.x >> 1;
+    const int pair = (int)blockIdx.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            const uint32_t lead_full0 = full_bar(0) & PEER_MASK;
+            for (int it = 0; it < iters; ++it) {
+                const int t = pair + it * n_pairs;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    if (leader) mbar_expect_tx(full_bar(s), 2 * PAIR_STAGE_BYTES);  // both CTAs' halves
+                    const uint32_t dst = smem0 + s * PAIR_STAGE_BYTES;
+                    const uint32_t lbar = lead_full0 + (uint32_t)s * 8u;
+                    tma_load_2d_pair(dst, &tmap_q, lbar, kb * BLOCK_K, (int)crank * BLOCK_Q);
+                    tma_load_2d_pair(dst + QTILE_BYTES, &tmap_r, lbar, kb * BLOCK_K, t * PAIR_N + (int)crank * 128);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            int buf = 0;
+            uint32_t bph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(tempty_bar(buf), bph ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem0 + s * PAIR_STAGE_BYTES;
+                    const uint64_t adesc = smem_desc(a0);
+                    const uint64_t bdesc = smem_desc(a0 + QTILE_BYTES);
+                    const uint32_t d = tmem_base + buf * ACC_COLS;
+#pragma unroll
+                    for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
+                        umma_bf16_pair(d, adesc + 2 * k4, bdesc + 2 * k4, IDESC_PAIR, (kb | k4) != 0);
+                    umma_commit_pair(empty_bar(s));
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+                umma_commit_pair(tfull_bar(buf));
+                buf ^= 1;
+                if (buf == 0) bph ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        const int qi = (int)crank * BLOCK_Q + quarter * 32 + lane;   // this thread's query
+        const bool active = qi < nq;
+        const int64_t slot = (int64_t)blockIdx.x * MAX_Q + qi;
+        uint64_t* buf_keys = cand_keys + slot * CAP;
+        int cnt = active ? cand_cnt[slot] : 0;
+        float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
+        if (!active) thr = INFINITY;
+        float t0 = -INFINITY, t1 = -INFINITY;
+        const bool sample_only = tops != nullptr;
+        const bool l2 = q_sqnorm != nullptr;
+        const float l2_bias = (l2 && active) ? 1.f - q_sqnorm[qi] : 0.f;
+        const uint32_t* qmask = mask ? mask + (active ? (int64_t)qi * mask_q_stride : 0) : nullptr;
+        int buf = 0;
+        uint32_t bph = 0;
+        for (int it = 0; it < iters; ++it) {
+            const int t = pair + it * n_pairs;
+            mbar_wait(tfull_bar(buf), bph);
+            tc_fence_after();
+            const int64_t row0 = (int64_t)t * PAIR_N;
+#pragma unroll 1
+            for (int c = 0; c < PAIR_N / 32; ++c) {
+                unsigned need = __ballot_sync(YRB_FULL, cnt > CAP - 32);
+                while (need) {
+                    const int L = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int n = __shfl_sync(YRB_FULL, cnt, L);
+                    const uint64_t base = shfl_u64((uint64_t)buf_keys, L);
+                    uint64_t* bp = reinterpret_cast<uint64_t*>(base);
+                    uint64_t v[8];
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (i * 32 + lane < n) ? bp[i * 32 + lane] : 0ull;
+                    warp_sort256_desc(v, lane);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i * 32 + lane < k) bp[i * 32 + lane] = v[i];
+                    uint64_t kth = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint64_t x = shfl_u64(v[i], (k - 1) & 31);
+                        if (((k - 1) >> 5) == i) kth = x;
+                    }
+                    __syncwarp();
+                    if (lane == L) {
+                        cnt = n < k ? n : k;
+                        if (n >= k) thr = key_score(kth);
+                    }
+                }
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + c * 32, v);
+                const int64_t r0 = row0 + c * 32;
+                uint32_t mw = 0u;
+                if (r0 < n_rows) {
+                    mw = qmask ? qmask[r0 >> 5] : 0xffffffffu;
+                    if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
+                    if (l2) {
+                        const float4* xn = reinterpret_cast<const float4*>(row_sqnorm + r0);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 n4 = xn[j4];
+                            v[4 * j4 + 0] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 0]), l2_bias - n4.x));
+                            v[4 * j4 + 1] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 1]), l2_bias - n4.y));
+                            v[4 * j4 + 2] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 2]), l2_bias - n4.z));
+                            v[4 * j4 + 3] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 3]), l2_bias - n4.w));
+                        }
+                    }
+                }
+                if (sample_only) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (((mw >> j) & 1u) && s > t1) {
+                            if (s > t0) {
+                                t1 = t0;
+                                t0 = s;
+                            } else {
+                                t1 = s;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = __uint_as_float(v[j]);
+                        if (((mw >> j) & 1u) && s > thr) buf_keys[cnt++] = make_key(s, (uint32_t)(r0 + j));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader) mbar_arrive(tempty_bar(buf));
+                else mbar_arrive_remote(tempty_bar(buf), 0);
+            }
+            buf ^= 1;
+            if (buf == 0) bph ^= 1;
+        }
+        if (active) {
+            if (!sample_only) cand_cnt[slot] = cnt;
+            if (tops) {
+                tops[((int64_t)blockIdx.x * MAX_TOPS + 0) * MAX_Q + qi] = t0;
+                if (m_tops > 1) tops[((int64_t)blockIdx.x * MAX_TOPS + 1) * MAX_Q + qi] = t1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+}  // namespace k2
+
+cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks, int iters,
+                             int nq, int k, const uint32_t* mask, int64_t mask_q_stride, const float* thr, uint64_t* ck,
+                             int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm,
+                             cudaStream_t st) {
+    const size_t smem = (size_t)k2::PAIR_STAGES * k2::PAIR_STAGE_BYTES + 1024;
+    cudaError_t e = cudaFuncSetAttribute(k2::k2_gemm_topk_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k2::k2_gemm_topk_pair<<<grid, 256, smem, st>>>(mq, mr, n_rows, kblocks, iters, nq, k, mask, mask_q_stride, thr, ck, cc,
+                                                   tops, m_tops, q_sqnorm, row_sqnorm);
+    return cudaGetLastError();
+}
+
+}  // namespace yrb
