@@ -173,7 +173,8 @@ YRB_API int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int part
                           int32_t* dev_out_counts, void* stream);
 
 /* Force a kernel family for tests/bench: 0 auto, 1 K1 (GEMV + in-register top-k),
- * 2 K2 (tcgen05 GEMM + fused top-k epilogue), 3 K6 (score matrix + radix select). */
+ * 2 K2 (tcgen05 GEMM + fused top-k epilogue), 3 K6 (key vector + radix select),
+ * 4 K2 with 129..256-query chunks on the CTA-pair (cta_group::2) kernel. */
 YRB_API int yrb_index_set_path(yrb_index* ix, int path);
 /* launches issued by this index since creation (bench `gpu_launches`), and the duration in ms of
  * the dominant kernel of the last search measured with CUDA events when enabled. */

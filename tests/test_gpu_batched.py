@@ -160,3 +160,29 @@ def test_per_query_filters(nq):
         check_topk(ids, sc, rows, ox.prepare(q, "cosine", "bf16")[0], 3, "cosine", "bf16", mask=mask)
         single = asyncio.run(s.search(q.tolist(), top_k=3, filters=filters[j]))
         assert [c.id for c, _ in single] == [c.id for c, _ in got[j]]
+
+
+def test_k2_pair_kernel_matches_single_cta_kernel():
+    """cta_group::2 pair kernel (path 4) vs the one-CTA kernel (path 2) vs the oracle, incl. masks and euclidean."""
+    n, d, nq = 70000, 512, 200
+    x = unit_rows(n, d, 51)
+    x[[9, 40000]] = x[9]
+    qs = unit_rows(nq, d, 52)
+    qs[130] = x[9]
+    mask = np.random.default_rng(53).random(n) < 0.2
+    mask[[9, 40000]] = True
+    for metric in ("cosine", "euclidean"):
+        ix = build(x, metric)
+        rows = ix.read_rows(np.arange(n))
+        for m in (None, mask):
+            pm = None if m is None else ox.pack_mask(m)
+            ix.set_path(native.PATH_K2_PAIR)
+            a = ix.search(qs, 50, mask=pm)
+            ix.set_path(native.PATH_K2)
+            b = ix.search(qs, 50, mask=pm)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+            for j in (0, 127, 128, 130, 199):
+                check_topk(a[0][j], a[1][j], rows, ox.prepare(qs[j], metric, "bf16")[0], 50, metric, "bf16", mask=m,
+                           tie_eps=2e-5 if metric == "euclidean" else None)
+            if metric == "cosine":
+                assert a[0][130, :2].tolist() == [9, 40000]

@@ -417,6 +417,8 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         else if (nq >= 8 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
         else path = 1;
     }
+    const bool pair = (path == 4);
+    if (pair) path = 2;
     if (path == 2 && !yrb::k2_supported(ix->dtype, ix->dim, k))
         return fail(YRB_ERR_UNSUPPORTED, "K2 (tcgen05 batched) needs bf16 storage and k <= %d", YRB_FUSED_K_MAX);
     if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
@@ -429,7 +431,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         if (rc) return rc;
         rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
                             mask_q_stride, ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, ix->sm_count, st,
-                            &launches, g_err, ea, eb);
+                            &launches, g_err, ea, eb, pair);
         ix->launches += launches;
         return rc;
     }
@@ -978,7 +980,7 @@ int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int n
 
 int yrb_index_set_path(yrb_index* ix, int path) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
-    if (path < 0 || path > 3) return fail(YRB_ERR_INVALID, "path must be 0..3");
+    if (path < 0 || path > 4) return fail(YRB_ERR_INVALID, "path must be 0..4");
     ix->path = path;
     return YRB_OK;
 }

@@ -43,8 +43,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     k2_gemm_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows,
                  int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
-                 float* __restrict__ tops, int m_tops, const unsigned char* __restrict__ rows_base, int row_bytes,
-                 int prefetch, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
+                 float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
                  int64_t mask_q_stride) {
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
@@ -100,17 +99,6 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             uint32_t ph = 0;
             for (int t = first; t < tile_end; t += step) {
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    if (prefetch) {
-                        // stream the NEXT tile of this CTA into L2 as whole rows, 1/kblocks of it per k-block
-                        const int64_t nt = (int64_t)t + step;
-                        const int rows_per = (BLOCK_R + kblocks - 1) / kblocks;
-                        const int64_t r0 = nt * BLOCK_R + (int64_t)kb * rows_per;
-                        int64_t r1 = r0 + rows_per;
-                        if (r1 > (nt + 1) * BLOCK_R) r1 = (nt + 1) * BLOCK_R;
-                        if (r1 > n_rows) r1 = n_rows;
-                        if (nt < tile_end && r1 > r0)
-                            prefetch_l2(rows_base + r0 * row_bytes, (uint32_t)((r1 - r0) * row_bytes));
-                    }
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), SB);
                     const uint32_t dst = smem0 + s * SB;
@@ -143,13 +131,16 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     tc_fence_after();
                     const uint32_t a0 = smem0 + s * SB;
                     const uint64_t bdesc = smem_desc(a0 + QB * QTILE_BYTES);
+                    // the two query blocks accumulate into different TMEM tiles: alternate them so that
+                    // consecutive MMAs never depend on each other's accumulator
 #pragma unroll
-                    for (int qb = 0; qb < QB; ++qb) {
-                        const uint64_t adesc = smem_desc(a0 + qb * QTILE_BYTES);
-                        const uint32_t d = tmem_base + buf * ACC_COLS + qb * BLOCK_R;
+                    for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
 #pragma unroll
-                        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
+                        for (int qb = 0; qb < QB; ++qb) {
+                            const uint64_t adesc = smem_desc(a0 + qb * QTILE_BYTES);
+                            const uint32_t d = tmem_base + buf * ACC_COLS + qb * BLOCK_R;
                             umma_bf16(d, adesc + 2 * k4, bdesc + 2 * k4, IDESC, (kb | k4) != 0);
+                        }
                     }
                     if (CL == 1) umma_commit(empty_bar(s));
                     else umma_commit_mcast(empty_bar(s), cmask);
@@ -366,8 +357,7 @@ static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows
 template <int QB>
 static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows,
                                int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
-                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const void* rows_base,
-                               int row_bytes, const float* q_sqnorm, const float* row_sqnorm, int64_t mask_q_stride,
+                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm, int64_t mask_q_stride,
                                cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
@@ -385,17 +375,15 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    static int pf = -1;
-    if (pf < 0) pf = getenv("YRB_K2_PREFETCH") ? atoi(getenv("YRB_K2_PREFETCH")) : 1;
     return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
-                              reinterpret_cast<const unsigned char*>(rows_base), row_bytes, pf, q_sqnorm, row_sqnorm, mask_q_stride);
+                              q_sqnorm, row_sqnorm, mask_q_stride);
 }
 
 // CTA-pair kernel for 129..256-query chunks (YRB_K2_PAIR=0 keeps the one-CTA kernel)
-static bool k2_use_pair() {
+static bool k2_use_pair(bool forced) {
     static int v = -1;
-    if (v < 0) v = getenv("YRB_K2_PAIR") ? atoi(getenv("YRB_K2_PAIR")) : 1;
-    return v != 0;
+    if (v < 0) v = getenv("YRB_K2_PAIR") ? atoi(getenv("YRB_K2_PAIR")) : 0;
+    return forced || v != 0;
 }
 
 // cluster size for the query multicast: 2 always packs the 148 SMs (74 TPCs); override with YRB_K2_CLUSTER
@@ -414,7 +402,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               int k, const uint32_t* mask_all, int64_t mask_q_stride, int metric, const float* q_sqnorm,
               const float* row_sqnorm, uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
               int* launches, std::string& err,
-              cudaEvent_t ev_start, cudaEvent_t ev_stop) {
+              cudaEvent_t ev_start, cudaEvent_t ev_stop, bool force_pair) {
     (void)capacity; (void)dim;
     const float* xn = metric == YRB_METRIC_L2 ? row_sqnorm : nullptr;
     if (!s->encode) {
@@ -450,7 +438,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
         const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
         const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
-        if (nqc > k2::BLOCK_Q && k2_use_pair()) {
+        if (nqc > k2::BLOCK_Q && k2_use_pair(force_pair)) {
             // CTA pairs (cta_group::2): 256-row tiles, CTA r of a pair owns queries [128r, 128r+128)
             const int tiles2 = (int)((n_rows + 255) / 256);
             int n_pairs = sm_count / 2;
@@ -502,10 +490,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (sampled) {
             if (QB == 2)
                 K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, qn, xn, mask_q_stride, st));
+                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, st));
             else
                 K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, rows, ld * 2, qn, xn, mask_q_stride, st));
+                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, st));
             k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0, 1);
             K2CK(cudaGetLastError());
             *launches += 2;
@@ -516,10 +504,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
         if (QB == 2)
             K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, rows, ld * 2, qn, xn, mask_q_stride, st));
+                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, st));
         else
             K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, rows, ld * 2, qn, xn, mask_q_stride, st));
+                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, st));
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
         const int gridB = grid;
         K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,

@@ -18,7 +18,8 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               int k, const uint32_t* mask, int64_t mask_q_stride /*words between queries' masks, 0 = shared*/, int metric,
               const float* q_sqnorm, const float* row_sqnorm,
               uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st, int* launches, std::string& err,
-              cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr);  // recorded around the main GEMM launch
+              cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr,  // recorded around the main GEMM launch
+              bool force_pair = false);  // 129..256-query chunks on the cta_group::2 kernel
 
 // pair kernel (k2_pair.cu)
 }  // namespace yrb

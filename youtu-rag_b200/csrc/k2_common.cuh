@@ -69,10 +69,6 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
-// contiguous bulk prefetch into L2 (whole rows: DRAM-page friendly, unlike the 128-byte column slabs of a box)
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -22,7 +22,7 @@ DTYPES = {"bf16": 0, "f32": 1}
 COL_I64, COL_F64, COL_CODE, COL_BOOL = 0, 1, 2, 3
 OPS = {"$eq": 0, "$ne": 1, "$gt": 2, "$gte": 3, "$lt": 4, "$lte": 5, "$in": 6, "$nin": 7}
 TOK_AND, TOK_OR, TOK_NOT = -1, -2, -3
-PATH_AUTO, PATH_K1, PATH_K2, PATH_K6 = 0, 1, 2, 3
+PATH_AUTO, PATH_K1, PATH_K2, PATH_K6, PATH_K2_PAIR = 0, 1, 2, 3, 4
 FUSED_K_MAX = 128
 WHERE_MAX_LEAVES, WHERE_MAX_OPERANDS, WHERE_MAX_TOKENS = 64, 256, 160
 
