@@ -200,7 +200,8 @@ int ensure_scratch(yrb_index* ix, int nq, int k) {
     const int parts = std::max(yrb::k1_parts(ix->sm_count), yrb::k2_parts(ix->sm_count));
     const size_t es = yrb::elem_size(ix->dtype);
     CK(cudaMalloc(&ix->d_qf32, (size_t)nqc * ix->dim * 4));
-    CK(cudaMalloc(&ix->d_q, (size_t)nqc * ix->ld * es));
+    // prepared queries, padded to whole 128-query blocks (zero rows) so K2's TMA boxes never leave the tensor
+    CK(cudaMalloc(&ix->d_q, (size_t)((nqc + 127) / 128 * 128) * ix->ld * es));
     CK(cudaMalloc(&ix->d_qsq, (size_t)nqc * 4));
     CK(cudaMalloc(&ix->d_parts, (size_t)parts * nqc * kc * 8));
     CK(cudaMalloc(&ix->d_keys, (size_t)nqc * kc * 8));
@@ -414,7 +415,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
     int path = ix->path;
     if (path == 0) {
         if (k > YRB_FUSED_K_MAX) path = 3;
-        else if (nq >= 8 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;
+        else if (nq >= 2 && yrb::k2_supported(ix->dtype, ix->dim, k)) path = 2;  // K2 beats a K1 loop from 2 queries (scripts/crossover.py)
         else path = 1;
     }
     const bool pair = (path == 4);
@@ -425,6 +426,10 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
     if (path == 2) {
         CK(yrb::launch_ingest(dev_q, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
+        const int nq_pad = (nq + 127) / 128 * 128;
+        if (nq_pad > nq)
+            CK(cudaMemsetAsync(reinterpret_cast<char*>(ix->d_q) + (size_t)nq * ix->ld * yrb::elem_size(ix->dtype), 0,
+                               (size_t)(nq_pad - nq) * ix->ld * yrb::elem_size(ix->dtype), st));
         int launches = 1;
         cudaEvent_t ea, eb;
         int rc = prof_pair(ix, &ea, &eb);

@@ -445,7 +445,8 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             if (tiles2 < n_pairs) n_pairs = tiles2;
             const int grid2 = 2 * n_pairs;
             CUtensorMap mq2;
-            if (!make_map(s, &mq2, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld, k2::BLOCK_Q, err))
+            if (!make_map(s, &mq2, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)((nqc + 127) / 128 * 128), ld,
+                          k2::BLOCK_Q, err))
                 return YRB_ERR_CUDA;
             K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)s->slots * k2::MAX_Q * 4, st));
             const int m_tops2 = (2 * k + n_pairs - 1) / n_pairs <= 1 ? 1 : k2::MAX_TOPS;
@@ -477,7 +478,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         const int cluster = k2_cluster(sm_count);
         grid = (grid + cluster - 1) / cluster * cluster;
         CUtensorMap mq;
-        if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)nqc, ld,
+        if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)((nqc + 127) / 128 * 128), ld,
                       QB * k2::BLOCK_Q / cluster, err))
             return YRB_ERR_CUDA;
         K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)s->slots * k2::MAX_Q * 4, st));
