@@ -59,13 +59,20 @@ class ShardedSearcher:
         key = (nq, k)
         if key not in self._bufs:
             dev = self.device
-            self._bufs[key] = [dict(
-                local=torch.zeros(nq * k, dtype=torch.int64, device=dev),
-                gathered=torch.zeros(self.world * nq * k, dtype=torch.int64, device=dev),
-                ids=torch.empty(nq * k, dtype=torch.int64, device=dev),
-                scores=torch.empty(nq * k, dtype=torch.float32, device=dev),
-                counts=torch.empty(nq, dtype=torch.int32, device=dev),
-                scanned=torch.cuda.Event(), merged=torch.cuda.Event()) for _ in range(self.depth)]
+            slots = []
+            for _ in range(self.depth):
+                # ids | scores | counts in ONE device buffer (and one pinned mirror): a host search ends with one D2H copy
+                packed = torch.empty(nq * k * 12 + nq * 4, dtype=torch.uint8, device=dev)
+                slots.append(dict(
+                    local=torch.zeros(nq * k, dtype=torch.int64, device=dev),
+                    gathered=torch.zeros(self.world * nq * k, dtype=torch.int64, device=dev),
+                    packed=packed, host=torch.empty(packed.shape, dtype=torch.uint8, pin_memory=True),
+                    ids=packed[: nq * k * 8].view(torch.int64),
+                    scores=packed[nq * k * 8: nq * k * 12].view(torch.float32),
+                    counts=packed[nq * k * 12:].view(torch.int32),
+                    scanned=torch.cuda.Event(), merged=torch.cuda.Event()))
+            self._bufs[key] = slots
+            self._hq = {}
         return self._bufs[key]
 
     def search_device(self, dev_queries: torch.Tensor, k: int, dev_mask: torch.Tensor | None = None):
@@ -100,14 +107,29 @@ class ShardedSearcher:
         self.comm_stream.synchronize()
 
     def search(self, queries: np.ndarray, k: int, dev_mask: torch.Tensor | None = None):
-        """Host in / host out (pinned staging is torch's)."""
+        """Host in / host out: pinned staging both ways, one H2D and one D2H copy."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        slots = self._buffers(nq, k)
+        stage = self._hq.get(nq)
+        if stage is None:
+            stage = self._hq[nq] = (torch.empty(q.shape, dtype=torch.float32, pin_memory=True),
+                                    torch.empty(q.shape, dtype=torch.float32, device=self.device))
+        stage[0].numpy()[...] = q
         with torch.cuda.stream(self.stream):
-            q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32)).to(self.device, non_blocking=True)
-        self.stream.synchronize()
-        ids, scores, counts = self.search_device(q, k, dev_mask)
+            stage[1].copy_(stage[0], non_blocking=True)
+        b = slots[self._turn % self.depth]
+        self.search_device(stage[1], k, dev_mask)
         with torch.cuda.stream(self.comm_stream):
-            out = ids.cpu().numpy(), scores.cpu().numpy(), counts.cpu().numpy()
-        return out
+            b["host"].copy_(b["packed"], non_blocking=True)
+        self.comm_stream.synchronize()
+        h = b["host"].numpy()
+        ids = h[: nq * k * 8].view(np.int64).reshape(nq, k).copy()
+        scores = h[nq * k * 8: nq * k * 12].view(np.float32).reshape(nq, k).copy()
+        counts = h[nq * k * 12:].view(np.int32).copy()
+        return ids, scores, counts
 
 
 # ------------------------------------------------------------------ host-side exchange (gloo tests)
