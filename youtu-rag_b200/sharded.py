@@ -54,6 +54,7 @@ class ShardedSearcher:
             self.stream = torch.cuda.Stream(self.device)
             self.comm_stream = torch.cuda.Stream(self.device, priority=-1) if self.world > 1 else self.stream
         self._bufs = {}
+        self._hq = {}
 
     def _buffers(self, nq: int, k: int):
         key = (nq, k)
@@ -72,7 +73,6 @@ class ShardedSearcher:
                     counts=packed[nq * k * 12:].view(torch.int32),
                     scanned=torch.cuda.Event(), merged=torch.cuda.Event()))
             self._bufs[key] = slots
-            self._hq = {}
         return self._bufs[key]
 
     def search_device(self, dev_queries: torch.Tensor, k: int, dev_mask: torch.Tensor | None = None):
