@@ -240,7 +240,7 @@ def run_b200(args):
 
     hq = host_queries(dim, nq)
     dq = torch.from_numpy(hq).to(dev)
-    searcher = ShardedSearcher(index, bounds)
+    searcher = ShardedSearcher(index, bounds, exchange=args.exchange)
     st = searcher.stream  # every kernel of a step is launched on this stream
 
     def step_device(i):
@@ -368,7 +368,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": nq * k * 12 + nq * 4, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "steps": e2e_steps, "api": "yrb_index_search (C ABI, host buffers)" if world == 1 and dev_mask is None
                     else "ShardedSearcher.search (host buffers)"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "exchange": searcher.exchange_kind,
         }
         print(json.dumps(line))
     if world > 1:
@@ -384,6 +384,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", type=int, default=0, help="force kernel family: 1 K1, 2 K2, 3 K6")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU top-k exchange: p2p = one kernel over NVLink peer memory (K7), nccl = all-gather + merge")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

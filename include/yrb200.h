@@ -172,6 +172,23 @@ YRB_API int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int part
                           const int64_t* dev_row_base, int64_t* dev_out_ids, float* dev_out_scores,
                           int32_t* dev_out_counts, void* stream);
 
+/* The same collective as ONE kernel over NVLink peer memory (kernel K7): every rank stores its keys
+ * directly into all peers' gather buffers (CUDA-IPC mapped), raises per-query flags, waits for the
+ * peers' flags and merges — no NCCL call, no host-side collective enqueue.  One process per GPU:
+ * create() allocates this rank's buffers and returns yrb_exchange_handle_bytes() bytes of IPC handles;
+ * the caller all-gathers the handles of all ranks (any transport) and passes them to connect().
+ * merge() must be called by every rank, in the same order, with the same nq and k. */
+typedef struct yrb_exchange yrb_exchange;
+YRB_API int yrb_exchange_handle_bytes(void);
+YRB_API const char* yrb_exchange_last_error(void);
+YRB_API int yrb_exchange_create(yrb_exchange** out, int device, int world, int rank, int nq_cap, int k_cap,
+                                unsigned char* out_handles);
+YRB_API int yrb_exchange_connect(yrb_exchange* ex, const unsigned char* all_handles /* world * handle_bytes */);
+YRB_API int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq, int k,
+                               const int64_t* dev_row_base, int64_t* dev_out_ids, float* dev_out_scores,
+                               int32_t* dev_out_counts, void* stream);
+YRB_API int yrb_exchange_destroy(yrb_exchange* ex);
+
 /* Force a kernel family for tests/bench: 0 auto, 1 K1 (GEMV + in-register top-k),
  * 2 K2 (tcgen05 GEMM + fused top-k epilogue), 3 K6 (key vector + radix select),
  * 4 K2 with 129..256-query chunks on the CTA-pair (cta_group::2) kernel. */

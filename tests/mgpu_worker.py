@@ -29,7 +29,17 @@ def main():
     ix.append(x[a:b])
     rows = ox.prepare(x, "cosine", "bf16")
     assert np.array_equal(ix.read_rows(np.arange(b - a)).view(np.uint32), rows[a:b].view(np.uint32))
-    s = ShardedSearcher(ix, bounds)
+    kinds = {}
+    for want in ("p2p", "nccl"):
+        _run(ShardedSearcher(ix, bounds, exchange=want), want, kinds, x, rows, n, d, a, b, world)
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_OK world", world, "exchanges", kinds)
+    dist.destroy_process_group()
+
+
+def _run(s, want, kinds, x, rows, n, d, a, b, world):
+    kinds[want] = s.exchange_kind
     mask = np.random.default_rng(2).random(n) < 0.2
     mask[[7, n - 1]] = True
     local_words = torch.from_numpy(ox.pack_mask(np.concatenate([mask[a:b], np.zeros((-(b - a)) % 64, bool)])).view(np.int32)).cuda()
@@ -41,10 +51,7 @@ def main():
                 c = int(counts[j])
                 check_topk(ids[j, :c], scores[j, :c], rows, ox.prepare(qs[j], "cosine", "bf16")[0], k, "cosine", "bf16", mask=m)
             assert ids[0, :2].tolist() == [7, n - 1]
-    dist.barrier()
-    if rank == 0:
-        print("MGPU_OK world", world)
-    dist.destroy_process_group()
+    s.synchronize()
 
 
 if __name__ == "__main__":

@@ -33,7 +33,8 @@ EXPORTS = (
     "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_read_raw", "yrb_index_append_raw", "yrb_index_set_live", "yrb_index_clear",
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
-    "yrb_merge_topk_device", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
+    "yrb_merge_topk_device", "yrb_exchange_handle_bytes", "yrb_exchange_last_error", "yrb_exchange_create",
+    "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
     "yrb_index_profile_read",
 )
 
@@ -92,13 +93,18 @@ def lib() -> C.CDLL:
     L.yrb_index_search_device.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.yrb_index_search_device_ids.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_merge_topk_device.argtypes = [i32, vp, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.yrb_exchange_last_error.restype = C.c_char_p
+    L.yrb_exchange_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp]
+    L.yrb_exchange_connect.argtypes = [vp, vp]
+    L.yrb_exchange_merge.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.yrb_exchange_destroy.argtypes = [vp]
     L.yrb_index_set_path.argtypes = [vp, i32]
     L.yrb_index_stats.argtypes = [vp, C.POINTER(i64)]
     L.yrb_index_profile.argtypes = [vp, i32]
     L.yrb_index_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("yrb_last_error",):
+        if name not in ("yrb_last_error", "yrb_exchange_last_error"):
             fn.restype = i32
     if L.yrb_abi_version() != 1:
         raise RuntimeError(f"libyrb200.so ABI {L.yrb_abi_version()} != 1")
@@ -288,6 +294,43 @@ def merge_topk_device(device: int, dev_keys: int, parts: int, nq: int, k: int, d
                       dev_scores: int, dev_counts: int, stream: int = 0) -> None:
     _ck(lib().yrb_merge_topk_device(device, dev_keys, parts, nq, k, dev_row_base, dev_ids, dev_scores,
                                     dev_counts or None, stream or None))
+
+
+class Exchange:
+    """K7: the merge collective over NVLink peer memory (opaque `yrb_exchange*`)."""
+
+    def __init__(self, device: int, world: int, rank: int, nq_cap: int, k_cap: int):
+        self._h = C.c_void_p()
+        self.handle_bytes = lib().yrb_exchange_handle_bytes()
+        buf = (C.c_ubyte * self.handle_bytes)()
+        self._ckx(lib().yrb_exchange_create(C.byref(self._h), device, world, rank, nq_cap, k_cap, buf))
+        self.handles = bytes(buf)
+        self.world, self.nq_cap, self.k_cap = world, nq_cap, k_cap
+
+    @staticmethod
+    def _ckx(rc: int) -> None:
+        if rc != YRB_OK:
+            raise NativeError(rc, (lib().yrb_exchange_last_error() or b"").decode("utf-8", "replace"))
+
+    def connect(self, all_handles: bytes) -> None:
+        assert len(all_handles) == self.world * self.handle_bytes
+        buf = (C.c_ubyte * len(all_handles)).from_buffer_copy(all_handles)
+        self._ckx(lib().yrb_exchange_connect(self._h, buf))
+
+    def merge(self, dev_local_keys: int, nq: int, k: int, dev_row_base: int, dev_ids: int, dev_scores: int,
+              dev_counts: int, stream: int = 0) -> None:
+        self._ckx(lib().yrb_exchange_merge(self._h, dev_local_keys, nq, k, dev_row_base, dev_ids, dev_scores,
+                                           dev_counts or None, stream or None))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            try:
+                _lib.yrb_exchange_destroy(self._h)
+            except Exception:  # noqa: BLE001
+                pass
+            self._h = C.c_void_p()
+
+    __del__ = close
 
 
 def decode_keys(keys: np.ndarray) -> tuple[np.ndarray, np.ndarray]:

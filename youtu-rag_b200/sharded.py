@@ -37,7 +37,8 @@ class ShardedSearcher:
     queries; the latency of one search is unchanged).  With world == 1 there is no exchange and the
     scan kernel writes ids/scores itself (one launch per single-query search)."""
 
-    def __init__(self, index: native.Index | None, row_base: list[int], group=None, depth: int = 2):
+    def __init__(self, index: native.Index | None, row_base: list[int], group=None, depth: int = 2,
+                 exchange: str = "p2p", nq_cap: int = 1024, k_cap: int = 128):
         self.index = index
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -55,6 +56,28 @@ class ShardedSearcher:
             self.comm_stream = torch.cuda.Stream(self.device, priority=-1) if self.world > 1 else self.stream
         self._bufs = {}
         self._hq = {}
+        # exchange: "p2p" = K7, one kernel storing into peers' buffers over NVLink (CUDA IPC); "nccl" = all-gather
+        # + merge kernel.  p2p needs peer access between the GPUs; if it cannot be set up on EVERY rank, all ranks
+        # use NCCL (both are GPU paths).
+        self.exchange = None
+        self.exchange_kind = "none" if self.world == 1 else "nccl"
+        if self._cuda and self.world > 1 and exchange == "p2p":
+            k_cap = min(k_cap, 2048 // self.world)
+            ex, ok = None, 1
+            try:
+                ex = native.Exchange(index.device, self.world, self.rank, nq_cap, k_cap)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, ex.handles, group=group)
+                ex.connect(b"".join(handles))
+            except Exception as e:  # noqa: BLE001
+                ok = 0
+                self._p2p_error = repr(e)
+            flag = torch.tensor([ok], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.exchange, self.exchange_kind = ex, "p2p"
+            elif ex is not None:
+                ex.close()
 
     def _buffers(self, nq: int, k: int):
         key = (nq, k)
@@ -95,10 +118,14 @@ class ShardedSearcher:
         b["scanned"].record(self.stream)
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(b["scanned"])
-            dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
-            native.merge_topk_device(self.index.device, b["gathered"].data_ptr(), self.world, nq, k,
-                                     self._base_dev.data_ptr(), b["ids"].data_ptr(), b["scores"].data_ptr(),
-                                     b["counts"].data_ptr(), self.comm_stream.cuda_stream)
+            if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
+                self.exchange.merge(b["local"].data_ptr(), nq, k, self._base_dev.data_ptr(), b["ids"].data_ptr(),
+                                    b["scores"].data_ptr(), b["counts"].data_ptr(), self.comm_stream.cuda_stream)
+            else:
+                dist.all_gather_into_tensor(b["gathered"], b["local"], group=self.group)
+                native.merge_topk_device(self.index.device, b["gathered"].data_ptr(), self.world, nq, k,
+                                         self._base_dev.data_ptr(), b["ids"].data_ptr(), b["scores"].data_ptr(),
+                                         b["counts"].data_ptr(), self.comm_stream.cuda_stream)
             b["merged"].record(self.comm_stream)
         return b["ids"].view(nq, k), b["scores"].view(nq, k), b["counts"]
 
