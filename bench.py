@@ -327,7 +327,7 @@ def run_b200(args):
     launches_per_step = kern_n / args.steps
     if nq < 8 or args.path == 1:
         # K1: one launch scans the shard once for one query
-        algo_bytes = frac_rows * n_local * dim * 2 + (n_local / 8 if sel else 0) + dim * 2 + 148 * k * 8
+        algo_bytes = frac_rows * n_local * dim * 2 + (n_local / 8 if sel else 0) + dim * 4 + (148 if world == 1 else 146) * k * 8
         roof = {"bound": "hbm", "kernel": "k1_scan_topk", "achieved": algo_bytes / (kern_avg_ms * 1e-3) / 1e9,
                 "peak": hbm, "unit": "GB/s", "peak_source": peak_src, "bytes_per_launch": algo_bytes,
                 "avg_launch_ms": kern_avg_ms, "launches_per_step": launches_per_step, "traffic": traffic}

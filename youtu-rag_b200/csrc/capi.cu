@@ -96,6 +96,7 @@ struct yrb_index {
     size_t stage_bytes = 0;
     yrb::K2State* k2 = nullptr;
     int path = 0;
+    int reserved_sms = 0;
     int64_t launches = 0;
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
@@ -412,6 +413,7 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
 int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, int64_t mask_q_stride,
                 uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st) {
     const bool decode = ids != nullptr;
+    const int sms = std::max(2, ix->sm_count - ix->reserved_sms) & ~1;  // even: K2 runs CTA clusters of 2
     int path = ix->path;
     if (path == 0) {
         if (k > YRB_FUSED_K_MAX) path = 3;
@@ -435,13 +437,13 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         int rc = prof_pair(ix, &ea, &eb);
         if (rc) return rc;
         rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
-                            mask_q_stride, ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, ix->sm_count, st,
+                            mask_q_stride, ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, sms, st,
                             &launches, g_err, ea, eb, pair);
         ix->launches += launches;
         return rc;
     }
     if (path == 1) {
-        const int parts = yrb::k1_parts(ix->sm_count);
+        const int parts = yrb::k1_parts(sms);
         for (int j = 0; j < nq; ++j) {
             uint64_t* pk = ix->d_parts + (size_t)j * parts * k;
             yrb::K1Out o{out_keys + (size_t)j * k, ids ? ids + (size_t)j * k : nullptr,
@@ -450,7 +452,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             int rc = prof_mark(ix, st);
             if (rc) return rc;
             CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
-                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, k, pk, ix->d_ticket, o, &fused, ix->sm_count, st));
+                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, k, pk, ix->d_ticket, o, &fused, sms, st));
             if ((rc = prof_mark(ix, st))) return rc;
             ix->launches++;
             if (!fused) {
@@ -1007,6 +1009,14 @@ int yrb_index_profile_read(yrb_index* ix, double* out_total_ms, int64_t* out_lau
     if (out_launches) *out_launches = ix->prof_n;
     ix->prof_ms = 0.0;
     ix->prof_n = 0;
+    return YRB_OK;
+}
+
+int yrb_index_set_reserved_sms(yrb_index* ix, int n) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (n < 0 || n >= ix->sm_count) return fail(YRB_ERR_INVALID, "reserved SMs must be in [0, %d)", ix->sm_count);
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->reserved_sms = n;
     return YRB_OK;
 }
 

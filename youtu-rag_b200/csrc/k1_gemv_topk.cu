@@ -26,14 +26,7 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_R = 4;   // rows per batch
 constexpr int K1_CU = 4;  // chunks per unrolled step
 
-// CTAs of the scan.  YRB_K1_RESERVE_SMS leaves that many SMs free so that kernels of another stream
-// (the NCCL exchange of the previous search) can run beside the persistent scan.
-int k1_parts(int sm_count) {
-    static int reserve = -1;
-    if (reserve < 0) reserve = getenv("YRB_K1_RESERVE_SMS") ? atoi(getenv("YRB_K1_RESERVE_SMS")) : 0;
-    const int g = sm_count - reserve;
-    return g > 0 ? g : 1;
-}
+int k1_parts(int sm_count) { return sm_count; }
 
 template <bool F32>
 __device__ __forceinline__ float dot_chunk(uint4 v, float4 qa, float4 qb, float acc) {

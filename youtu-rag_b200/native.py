@@ -34,7 +34,7 @@ EXPORTS = (
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_exchange_handle_bytes", "yrb_exchange_last_error", "yrb_exchange_create",
-    "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_stats", "yrb_index_profile",
+    "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_set_reserved_sms", "yrb_index_stats", "yrb_index_profile",
     "yrb_index_profile_read",
 )
 
@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
     L.yrb_exchange_merge.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_exchange_destroy.argtypes = [vp]
     L.yrb_index_set_path.argtypes = [vp, i32]
+    L.yrb_index_set_reserved_sms.argtypes = [vp, i32]
     L.yrb_index_stats.argtypes = [vp, C.POINTER(i64)]
     L.yrb_index_profile.argtypes = [vp, i32]
     L.yrb_index_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
@@ -283,6 +284,9 @@ class Index:
         ms, n = C.c_double(), C.c_int64()
         _ck(lib().yrb_index_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def set_reserved_sms(self, n: int) -> None:
+        _ck(lib().yrb_index_set_reserved_sms(self._h, n))
 
     def launches(self) -> int:
         n = C.c_int64()

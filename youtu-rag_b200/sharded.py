@@ -54,6 +54,8 @@ class ShardedSearcher:
             # real (non-NULL) streams: the C ABI treats a NULL stream as "the index's own stream"
             self.stream = torch.cuda.Stream(self.device)
             self.comm_stream = torch.cuda.Stream(self.device, priority=-1) if self.world > 1 else self.stream
+            if self.world > 1:
+                index.set_reserved_sms(2)   # room for the exchange kernel beside the persistent scan
         self._bufs = {}
         self._hq = {}
         # exchange: "p2p" = K7, one kernel storing into peers' buffers over NVLink (CUDA IPC); "nccl" = all-gather
