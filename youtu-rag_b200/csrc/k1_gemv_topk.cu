@@ -283,8 +283,48 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             __threadfence();
             SelectArgs a{part_keys, k, 0, nullptr, 0, 0, (int)gridDim.x, k, k, nullptr, k, out.final_keys,
                          out.ids, out.scores, out.count};
-            SelectScratch& S = *reinterpret_cast<SelectScratch*>(smem_raw + (size_t)fuse_stage * 8);
-            select_topk_block(a, 0, sk, fuse_stage, S);
+            const int parts = (int)gridDim.x;
+            if (k <= 32 && parts <= 256) {
+                // small k: the per-CTA lists are sorted, so stage them (one parallel round of L2 reads) and let
+                // warp 0 run a k-step tournament over the list heads (lane l owns lists l, l+32, …).
+                for (int i = threadIdx.x; i < parts * k; i += blockDim.x) sk[i] = __ldcg(part_keys + i);
+                __syncthreads();
+                if (warp == 0) {
+                    int pos[8];
+                    uint64_t head[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        pos[j] = 0;
+                        const int l = lane + 32 * j;
+                        head[j] = l < parts ? sk[l * k] : 0ull;
+                    }
+                    int n_out = 0;
+                    for (int i = 0; i < k; ++i) {
+                        uint64_t best = head[0];
+#pragma unroll
+                        for (int j = 1; j < 8; ++j) best = head[j] > best ? head[j] : best;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const uint64_t other = shfl_xor_u64(best, o);
+                            best = other > best ? other : best;
+                        }
+                        if (lane == 0) select_emit(a, 0, i, best);
+                        n_out += best != 0ull;
+                        if (best != 0ull) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (head[j] == best) {   // unique keys: exactly one (lane, j) matches
+                                    ++pos[j];
+                                    head[j] = pos[j] < k ? sk[(lane + 32 * j) * k + pos[j]] : 0ull;
+                                }
+                        }
+                    }
+                    if (lane == 0 && a.out_counts) a.out_counts[0] = n_out;
+                }
+            } else {
+                SelectScratch& S = *reinterpret_cast<SelectScratch*>(smem_raw + (size_t)fuse_stage * 8);
+                select_topk_block(a, 0, sk, fuse_stage, S);
+            }
         }
     }
 }
