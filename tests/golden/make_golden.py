@@ -305,6 +305,23 @@ def run():
                     "batch": [[{"id": x.chunk.id, "score": x.score, "rank": x.rank} for x in b] for b in batch]})
 
     asyncio.run(go())
+    # ContextAssembler (context_assembler.py) over retriever-shaped results, run unmodified
+    pkg_name = "utu.rag.knowledge_retrieval.context_assembler"
+    ca = importlib.import_module(pkg_name)
+    RR, Ch = ref["base"].RetrievalResult, ref["base"].Chunk
+    hits = [RR(chunk=Ch(id=f"c{i}", document_id=f"d{i % 3}", content=f"内容 text {i} " * (i + 1), chunk_index=i,
+                        metadata=({"source": f"file{i % 2}.pdf", "chunk_index": i, "total_chunks": 9, "page": i} if i % 4 else None)),
+               score=1.0 - 0.07 * i, rank=i + 1) for i in range(8)]
+    out["assembler"] = {"hits": [{"id": h.chunk.id, "document_id": h.chunk.document_id, "content": h.chunk.content,
+                                  "chunk_index": h.chunk.chunk_index,
+                                  "metadata_items": list(h.chunk.metadata.items()) if h.chunk.metadata else None,  # key order matters
+                                  "score": h.score,
+                                  "rank": h.rank} for h in hits], "cases": []}
+    for style in ("markdown", "plain", "json"):
+        for inc in (True, False):
+            for budget in (4000, 300, 10):
+                out["assembler"]["cases"].append({"style": style, "include_metadata": inc, "max_len": budget,
+                                                  "text": ca.ContextAssembler(budget).assemble(hits, inc, style)})
     (HERE / "reference_glue.json").write_text(json.dumps(out, sort_keys=True, ensure_ascii=False, separators=(",", ":")))
     print("wrote", HERE / "reference_glue.json", len(out["chroma"]), "chroma cases,", len(out["faiss"]), "faiss cases")
 

@@ -69,3 +69,26 @@ def test_retriever_mirror_reproduces_reference_retriever():
         for got, want in [(single, rec["single"])] + list(zip(batch, rec["batch"])):
             assert [x.rank for x in got] == [w["rank"] for w in want]
             compare_with_golden([(x.chunk, x.score) for x in got], want, tol=2e-6)
+
+
+def test_context_assembler_reproduces_reference():
+    from youtu_rag_b200.base import Chunk, RetrievalResult
+    from youtu_rag_b200.postprocess import ContextAssembler, dedup_by_file, merge_results
+
+    g = GOLDEN["assembler"]
+    hits = [RetrievalResult(chunk=Chunk(id=h["id"], document_id=h["document_id"], content=h["content"],
+                                        chunk_index=h["chunk_index"],
+                                        metadata=dict(h["metadata_items"]) if h["metadata_items"] else None),
+                            score=h["score"], rank=h["rank"])
+            for h in g["hits"]]
+    for c in g["cases"]:
+        assert ContextAssembler(c["max_len"]).assemble(hits, c["include_metadata"], c["style"]) == c["text"], c
+    assert ContextAssembler().assemble([]) == ""
+    with pytest.raises(ValueError):
+        ContextAssembler().assemble(hits, format_style="xml")
+    files = dedup_by_file(hits, include_summary=True)
+    assert [f["file_name"] for f in files] == ["d0", "file1.pdf", "file0.pdf"]       # hit 0 has no metadata → document id
+    assert files[1]["chunk_id"] == "c1" and "chunk_index" not in files[1]["metadata"] and files[1]["summary"] == ""
+    dup = hits[:3] + [RetrievalResult(chunk=hits[1].chunk, score=0.99, rank=1)]
+    merged = merge_results(dup)
+    assert [(r.chunk.id, r.score) for r in merged] == [("c0", 1.0), ("c1", 0.99), ("c2", hits[2].score)]

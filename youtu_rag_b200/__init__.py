@@ -21,11 +21,12 @@ from .base import (  # noqa: E402
 from .config import RetrieverConfig, VectorStoreConfig  # noqa: E402
 from .factory import VectorStoreFactory  # noqa: E402
 from .memory_store import B200MemoryVectorStore, rank_memories, rank_skills  # noqa: E402
+from .postprocess import ContextAssembler, dedup_by_file, merge_results  # noqa: E402
 from .retriever import HybridRetriever, VectorRetriever  # noqa: E402
 from .store import B200VectorStore  # noqa: E402
 
 __all__ = [
-    "B200VectorStore", "B200MemoryVectorStore", "rank_memories", "rank_skills", "VectorStoreFactory", "VectorRetriever", "HybridRetriever", "VectorStoreConfig",
+    "B200VectorStore", "B200MemoryVectorStore", "rank_memories", "rank_skills", "VectorStoreFactory", "VectorRetriever", "HybridRetriever", "ContextAssembler", "dedup_by_file", "merge_results", "VectorStoreConfig",
     "RetrieverConfig", "BaseVectorStore", "BaseRetriever", "BaseEmbedder", "BaseReranker", "Chunk", "Document",
     "RetrievalResult",
 ]
