@@ -87,7 +87,7 @@ def test_context_assembler_reproduces_reference():
     with pytest.raises(ValueError):
         ContextAssembler().assemble(hits, format_style="xml")
     files = dedup_by_file(hits, include_summary=True)
-    assert [f["file_name"] for f in files] == ["d0", "file1.pdf", "file0.pdf"]       # hit 0 has no metadata → document id
+    assert [f["file_name"] for f in files] == ["d0", "file1.pdf", "file0.pdf", "d1"]  # no metadata → document id
     assert files[1]["chunk_id"] == "c1" and "chunk_index" not in files[1]["metadata"] and files[1]["summary"] == ""
     dup = hits[:3] + [RetrievalResult(chunk=hits[1].chunk, score=0.99, rank=1)]
     merged = merge_results(dup)
