@@ -145,3 +145,30 @@ def test_persistence_roundtrip_is_bit_identical(tmp_path):
     run(c.clear())
     assert not (tmp_path / "p.b200").exists()
     assert run(B200VectorStore(cfg).count()) == 0
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_c1_config_through_the_store(dtype):
+    """BASELINE.json configs[0]: 10k chunks x 1024-d unit embeddings, single query, top-10 cosine, via the
+    vector-store interface — against the exact oracle and the FAISS-semantics CPU restatement."""
+    from oracle import exact_search as ox
+    from tests.helpers import unit_rows
+    from youtu_rag_b200.base import Chunk
+
+    n, d = 10_000, 1024
+    x = unit_rows(n, d, 0)
+    s = B200VectorStore(VectorStoreConfig(collection_name="c1", distance_metric="cosine", index_params={"storage_dtype": dtype}))
+    for a in range(0, n, 2500):
+        run(s.add_chunks([Chunk(id=f"k{i}", document_id=f"doc{i // 100}", content=f"chunk {i}", chunk_index=i % 100,
+                                embedding=x[i].tolist()) for i in range(a, a + 2500)]))
+    assert run(s.count()) == n
+    rows = ox.prepare(x, "cosine", dtype)
+    for q in unit_rows(5, d, 1):
+        got = run(s.search(q.tolist(), top_k=10))
+        ids, scores = ox.exact_topk(rows, ox.prepare(q, "cosine", dtype)[0], 10, "cosine")
+        assert [c.id for c, _ in got] == [f"k{i}" for i in ids]
+        np.testing.assert_allclose([sc for _, sc in got], scores, rtol=1e-5 if dtype == "f32" else 1e-3, atol=1e-6)
+        if dtype == "f32":
+            f_ids, f_sim = ox.faiss_flat_search(ox.l2_normalize(x), q, 10, "cosine")     # the reference's exact variant
+            assert [c.id for c, _ in got] == [f"k{i}" for i in f_ids]
+            np.testing.assert_allclose([sc for _, sc in got], f_sim, rtol=1e-5, atol=1e-6)
