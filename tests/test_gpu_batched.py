@@ -186,3 +186,35 @@ def test_k2_pair_kernel_matches_single_cta_kernel():
                            tie_eps=2e-5 if metric == "euclidean" else None)
             if metric == "cosine":
                 assert a[0][130, :2].tolist() == [9, 40000]
+
+
+@pytest.mark.parametrize("sel", [0.0005, 0.02, 0.2, 0.3])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_k2_compaction_for_selective_shared_mask(sel, metric):
+    """>= 65536 rows and a shared mask passing <= 25 % of them: rows are gathered (K8) and K2 runs on the compact
+    matrix; 30 % stays on the dense masked path; 0.05 % (< k rows pass) falls back as well.  All must equal the oracle."""
+    n, d, nq, k = 100_003, 128, 40, 60
+    x = unit_rows(n, d, 61) * (1.0 if metric == "cosine" else 1.3)
+    mask = np.random.default_rng(62).random(n) < sel
+    x[[11, 70_000]] = x[11]
+    mask[[11, 70_000]] = True
+    ix = build(x, metric)
+    rows = ix.read_rows(np.arange(n))
+    qs = unit_rows(nq, d, 63)
+    qs[5] = x[11]
+    ids, scores, counts = ix.search(qs, k, mask=ox.pack_mask(mask))
+    for j in (0, 5, 39):
+        c = int(counts[j])
+        assert c == min(k, int(mask.sum()))
+        check_topk(ids[j, :c], scores[j, :c], rows, ox.prepare(qs[j], metric, "bf16")[0], k, metric, "bf16", mask=mask,
+                   tie_eps=2e-5 if metric == "euclidean" else None)
+    if metric == "cosine":
+        assert ids[5, :2].tolist() == [11, 70_000]
+    # tombstones ride in the same mask
+    dead = ids[0, :3].tolist()
+    ix.set_live(dead, False)
+    m2 = mask.copy(); m2[dead] = False
+    ids2, scores2, counts2 = ix.search(qs, k, mask=ox.pack_mask(mask))
+    c = int(counts2[0])
+    check_topk(ids2[0, :c], scores2[0, :c], rows, ox.prepare(qs[0], metric, "bf16")[0], k, metric, "bf16", mask=m2,
+               tie_eps=2e-5 if metric == "euclidean" else None)

@@ -77,6 +77,14 @@ struct yrb_index {
     float* d_scores = nullptr;
     int32_t* d_counts = nullptr;
     unsigned int* d_ticket = nullptr;   // K1's last-CTA-done counter
+    // K8 compaction scratch (grow-only)
+    uint32_t* d_cp_blocks = nullptr;
+    size_t cp_blocks_cap = 0;
+    void* d_cp_rows = nullptr;
+    float* d_cp_sqnorm = nullptr;
+    uint32_t* d_cp_map = nullptr;
+    int64_t cp_rows_cap = 0;
+    unsigned long long* h_pass = nullptr;  // pinned
     uint64_t* d_rowkeys = nullptr;  // K6: one key per row, allocated on first use
     int64_t rowkeys_cap = 0;
     void* d_select = nullptr;
@@ -427,6 +435,49 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
     if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
         return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
     if (path == 2) {
+        // K8: a filter shared by the batch that passes at most a quarter of the rows → gather the passing rows
+        // and run the GEMM on the compact matrix (needs the pass count on the host: one stream synchronisation)
+        const void* k2_rows = ix->d_rows;
+        const float* k2_sqnorm = ix->d_sqnorm;
+        int64_t k2_n = ix->rows;
+        bool compacted = false;
+        if (mask && mask_q_stride == 0 && ix->rows >= 65536) {
+            const size_t nb = yrb::compact_scratch_words(ix->rows);
+            if (nb > ix->cp_blocks_cap) {
+                CK(cudaStreamSynchronize(st));
+                FREE_DEV(ix->d_cp_blocks);
+                CK(cudaMalloc(&ix->d_cp_blocks, nb * 4));
+                ix->cp_blocks_cap = nb;
+            }
+            if (!ix->h_pass) CK(cudaMallocHost(&ix->h_pass, 8));
+            CK(yrb::launch_compact_count(mask, ix->rows, ix->d_cp_blocks, ix->d_pass, st));
+            CK(cudaMemcpyAsync(ix->h_pass, ix->d_pass, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ix->launches += 2;
+            const int64_t pass = (int64_t)*ix->h_pass;
+            if (pass >= k && pass <= ix->rows / 4) {
+                if (pass > ix->cp_rows_cap) {
+                    const int64_t cap = (pass + pass / 4 + 255) / 256 * 256;
+                    FREE_DEV(ix->d_cp_rows);
+                    FREE_DEV(ix->d_cp_sqnorm);
+                    FREE_DEV(ix->d_cp_map);
+                    ix->cp_rows_cap = 0;
+                    CK(cudaMalloc(&ix->d_cp_rows, (size_t)cap * ix->ld * yrb::elem_size(ix->dtype)));
+                    CK(cudaMalloc(&ix->d_cp_sqnorm, (size_t)cap * 4));
+                    CK(cudaMalloc(&ix->d_cp_map, (size_t)cap * 4));
+                    ix->cp_rows_cap = cap;
+                }
+                CK(yrb::launch_compact_gather(mask, ix->rows, ix->d_cp_blocks, ix->d_cp_map, ix->d_rows, ix->d_sqnorm,
+                                              ix->ld * yrb::elem_size(ix->dtype) / 16, pass, ix->d_cp_rows, ix->d_cp_sqnorm,
+                                              ix->sm_count, st));
+                ix->launches += 2;
+                k2_rows = ix->d_cp_rows;
+                k2_sqnorm = ix->d_cp_sqnorm;
+                k2_n = pass;
+                mask = nullptr;
+                compacted = true;
+            }
+        }
         CK(yrb::launch_ingest(dev_q, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
         const int nq_pad = (nq + 127) / 128 * 128;
         if (nq_pad > nq)
@@ -436,10 +487,14 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         cudaEvent_t ea, eb;
         int rc = prof_pair(ix, &ea, &eb);
         if (rc) return rc;
-        rc = yrb::k2_search(ix->k2, ix->d_rows, ix->rows, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
-                            mask_q_stride, ix->metric, ix->d_qsq, ix->d_sqnorm, out_keys, ids, scores, counts, sms, st,
+        rc = yrb::k2_search(ix->k2, k2_rows, k2_n, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
+                            mask_q_stride, ix->metric, ix->d_qsq, k2_sqnorm, out_keys, ids, scores, counts, sms, st,
                             &launches, g_err, ea, eb, pair);
         ix->launches += launches;
+        if (!rc && compacted) {
+            CK(yrb::launch_compact_remap(ix->d_cp_map, (int64_t)nq * k, out_keys, ids, st));
+            ix->launches++;
+        }
         return rc;
     }
     if (path == 1) {
@@ -596,6 +651,11 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_DEV(ix->d_progs);
     FREE_HOST(ix->h_progs);
     FREE_DEV(ix->d_qmasks);
+    FREE_DEV(ix->d_cp_blocks);
+    FREE_DEV(ix->d_cp_rows);
+    FREE_DEV(ix->d_cp_sqnorm);
+    FREE_DEV(ix->d_cp_map);
+    FREE_HOST(ix->h_pass);
     FREE_HOST(ix->h_prog);
     FREE_HOST(ix->h_stage);
     for (auto& kv : ix->cols) {

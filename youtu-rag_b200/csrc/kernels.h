@@ -84,6 +84,16 @@ cudaError_t launch_where(const WhereProgDev* prog, int64_t n_rows, const uint32_
 cudaError_t launch_mask_and(const uint32_t* a, const uint32_t* b, int64_t n_words, uint32_t* out,
                             cudaStream_t st);
 
+// ---- K8: row compaction for low-selectivity batched search (k8_compact.cu)
+size_t compact_scratch_words(int64_t n_rows);
+// block_sums gets the exclusive prefix of passing rows per 32768-row block, *total their number
+cudaError_t launch_compact_count(const uint32_t* mask, int64_t n_rows, uint32_t* block_sums, unsigned long long* total,
+                                 cudaStream_t st);
+cudaError_t launch_compact_gather(const uint32_t* mask, int64_t n_rows, const uint32_t* block_off, uint32_t* rowmap,
+                                  const void* rows, const float* sqnorm, int ld16, int64_t n_out, void* out_rows,
+                                  float* out_sqnorm, int sm_count, cudaStream_t st);
+cudaError_t launch_compact_remap(const uint32_t* rowmap, int64_t n, uint64_t* keys, int64_t* ids, cudaStream_t st);
+
 // ---- K6: any-k path (k <= 4096).  One 64-bit key per row for one query + radix select of the top k.
 cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                           const float* row_sqnorm, int metric,
