@@ -333,13 +333,15 @@ def run_b200(args):
                 "avg_launch_ms": kern_avg_ms, "launches_per_step": launches_per_step, "traffic": traffic}
     else:
         # the timed launch is K2's main GEMM (every tile of the shard, first 256-query chunk)
-        rows_b = n_local
+        # (a shared mask passing <= 25 % of the rows is compacted first by K8: the GEMM then covers the passing rows)
+        rows_b = n_pass if (sel and k <= n_pass <= n_local // 4) else n_local
         flops = 2.0 * min(nq, 256) * rows_b * dim
         roof = {"bound": "tensor", "kernel": "k2_gemm_topk (phase B launch)", "achieved": flops / (kern_avg_ms * 1e-3) / 1e12,
                 "peak": tf_burst, "unit": "TFLOP/s", "peak_source": peak_src, "flops_per_launch": flops,
                 "avg_launch_ms": kern_avg_ms, "launches_per_step": launches_per_step, "traffic": traffic,
                 "hbm_gbs_same_kernel": (rows_b * dim * 2) / (kern_avg_ms * 1e-3) / 1e9,
-                "note": "dense GEMM over all rows of the launch (masked rows are computed and dropped in the epilogue)"}
+                "rows_in_gemm": rows_b,
+                "note": "dense GEMM over rows_in_gemm rows (all rows, or the K8-compacted passing rows of a selective shared mask)"}
     roof["frac"] = roof["achieved"] / roof["peak"]
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only; bounded sample)
