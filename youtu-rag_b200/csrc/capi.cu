@@ -440,7 +440,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         const void* k2_rows = ix->d_rows;
         const float* k2_sqnorm = ix->d_sqnorm;
         int64_t k2_n = ix->rows;
-        bool compacted = false;
+        bool compacted = false, use_rowmap = false;
         if (mask && mask_q_stride == 0 && ix->rows >= 65536) {
             const size_t nb = yrb::compact_scratch_words(ix->rows);
             if (nb > ix->cp_blocks_cap) {
@@ -456,22 +456,32 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             ix->launches += 2;
             const int64_t pass = (int64_t)*ix->h_pass;
             if (pass >= k && pass <= ix->rows / 4) {
-                if (pass > ix->cp_rows_cap) {
+                // "gather4": K2 reads the passing rows in place through TMA tile::gather4 and the row map;
+                // "copy": the rows are first copied into a contiguous scratch matrix.
+                static int mode_g4 = -1;
+                if (mode_g4 < 0) mode_g4 = getenv("YRB_K8_MODE") ? (strcmp(getenv("YRB_K8_MODE"), "gather4") == 0) : 0;
+                use_rowmap = mode_g4 != 0;
+                if (pass > ix->cp_rows_cap || (!use_rowmap && !ix->d_cp_rows)) {
                     const int64_t cap = (pass + pass / 4 + 255) / 256 * 256;
                     FREE_DEV(ix->d_cp_rows);
                     FREE_DEV(ix->d_cp_sqnorm);
                     FREE_DEV(ix->d_cp_map);
                     ix->cp_rows_cap = 0;
-                    CK(cudaMalloc(&ix->d_cp_rows, (size_t)cap * ix->ld * yrb::elem_size(ix->dtype)));
-                    CK(cudaMalloc(&ix->d_cp_sqnorm, (size_t)cap * 4));
-                    CK(cudaMalloc(&ix->d_cp_map, (size_t)cap * 4));
+                    if (!use_rowmap) CK(cudaMalloc(&ix->d_cp_rows, (size_t)cap * ix->ld * yrb::elem_size(ix->dtype)));
+                    CK(cudaMalloc(&ix->d_cp_sqnorm, (size_t)(cap + 256) * 4));
+                    CK(cudaMalloc(&ix->d_cp_map, (size_t)(cap + 256) * 4));
                     ix->cp_rows_cap = cap;
                 }
                 CK(yrb::launch_compact_gather(mask, ix->rows, ix->d_cp_blocks, ix->d_cp_map, ix->d_rows, ix->d_sqnorm,
-                                              ix->ld * yrb::elem_size(ix->dtype) / 16, pass, ix->d_cp_rows, ix->d_cp_sqnorm,
-                                              ix->sm_count, st));
+                                              ix->ld * yrb::elem_size(ix->dtype) / 16, pass, use_rowmap ? nullptr : ix->d_cp_rows,
+                                              ix->d_cp_sqnorm, ix->sm_count, st));
                 ix->launches += 2;
-                k2_rows = ix->d_cp_rows;
+                if (use_rowmap) {
+                    // pad the map to whole 128-row tiles with a valid row; the epilogue ignores compact rows >= pass
+                    CK(cudaMemsetAsync(ix->d_cp_map + pass, 0, (size_t)((pass + 127) / 128 * 128 - pass) * 4, st));
+                } else {
+                    k2_rows = ix->d_cp_rows;
+                }
                 k2_sqnorm = ix->d_cp_sqnorm;
                 k2_n = pass;
                 mask = nullptr;
@@ -489,7 +499,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         if (rc) return rc;
         rc = yrb::k2_search(ix->k2, k2_rows, k2_n, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
                             mask_q_stride, ix->metric, ix->d_qsq, k2_sqnorm, out_keys, ids, scores, counts, sms, st,
-                            &launches, g_err, ea, eb, pair);
+                            &launches, g_err, ea, eb, pair, (compacted && use_rowmap) ? ix->d_cp_map : nullptr, ix->rows);
         ix->launches += launches;
         if (!rc && compacted) {
             CK(yrb::launch_compact_remap(ix->d_cp_map, (int64_t)nq * k, out_keys, ids, st));

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                  int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                  float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
-                 int64_t mask_q_stride) {
+                 int64_t mask_q_stride, const uint32_t* __restrict__ rowmap) {
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
     constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
@@ -94,7 +94,37 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     const int tile_end = first + iters * step;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (rowmap) {
+            // Row-subset mode (selective shared filter): tile t covers compact rows [128t, 128t+128) whose matrix
+            // rows are rowmap[...].  All 32 lanes take part: lane l gathers rows 4l..4l+3 of the tile with one
+            // tile::gather4 per k-block (tmap_r is then the gather map, box = one 64-element row).
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = first; t < tile_end; t += step) {
+                uint4 rr = make_uint4(0, 0, 0, 0);  // tiles past the end (equal trip counts) gather row 0 and are masked
+                if ((int64_t)t * BLOCK_R < n_rows) rr = reinterpret_cast<const uint4*>(rowmap)[(int64_t)t * (BLOCK_R / 4) + lane];
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (lane == 0) {
+                        mbar_wait(empty_bar(s), ph ^ 1);
+                        mbar_expect_tx(full_bar(s), SB);
+                        const uint32_t dq = smem0 + s * SB;
+                        const uint32_t piece_rows = (QB * BLOCK_Q) / CL;
+                        if (CL == 1)
+                            tma_load_2d(dq, &tmap_q, full_bar(s), kb * BLOCK_K, 0);
+                        else
+                            tma_load_2d_mcast(dq + crank * piece_rows * (BLOCK_K * 2), &tmap_q, full_bar(s), kb * BLOCK_K,
+                                              (int)(crank * piece_rows), cmask);
+                    }
+                    __syncwarp();
+                    tma_gather4(smem0 + s * SB + QB * QTILE_BYTES + lane * (4 * BLOCK_K * 2), &tmap_r, full_bar(s),
+                                kb * BLOCK_K, (int)rr.x, (int)rr.y, (int)rr.z, (int)rr.w);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        } else if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
             for (int t = first; t < tile_end; t += step) {
@@ -357,8 +387,8 @@ static bool make_map(K2State* s, CUtensorMap* m, const void* base, uint64_t rows
 template <int QB>
 static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows,
                                int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
-                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm, int64_t mask_q_stride,
-                               cudaStream_t st) {
+                               const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const float* q_sqnorm,
+                               const float* row_sqnorm, int64_t mask_q_stride, const uint32_t* rowmap, cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -376,7 +406,7 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
-                              q_sqnorm, row_sqnorm, mask_q_stride);
+                              q_sqnorm, row_sqnorm, mask_q_stride, rowmap);
 }
 
 // CTA-pair kernel for 129..256-query chunks (YRB_K2_PAIR=0 keeps the one-CTA kernel)
@@ -402,8 +432,9 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               int k, const uint32_t* mask_all, int64_t mask_q_stride, int metric, const float* q_sqnorm,
               const float* row_sqnorm, uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
               int* launches, std::string& err,
-              cudaEvent_t ev_start, cudaEvent_t ev_stop, bool force_pair) {
+              cudaEvent_t ev_start, cudaEvent_t ev_stop, bool force_pair, const uint32_t* rowmap, int64_t matrix_rows) {
     (void)capacity; (void)dim;
+    if (rowmap) force_pair = false;  // the row-subset producer lives in the one-CTA kernel
     const float* xn = metric == YRB_METRIC_L2 ? row_sqnorm : nullptr;
     if (!s->encode) {
         void* fn = nullptr;
@@ -431,14 +462,19 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
     const int kblocks = ld / k2::BLOCK_K;
     const int tiles = (int)((n_rows + k2::BLOCK_R - 1) / k2::BLOCK_R);
     CUtensorMap mr;
-    if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, k2::BLOCK_R, err)) return YRB_ERR_CUDA;
+    if (rowmap) {
+        // gather map over the WHOLE matrix: box = one row x 64 elements, rows chosen per instruction
+        static int gbox = -1;
+        if (gbox < 0) gbox = getenv("YRB_K2_GATHER_BOX") ? atoi(getenv("YRB_K2_GATHER_BOX")) : 1;
+        if (!make_map(s, &mr, rows, (uint64_t)matrix_rows, ld, gbox, err)) return YRB_ERR_CUDA;
+    } else if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, k2::BLOCK_R, err)) return YRB_ERR_CUDA;
 
     for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
         const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
         const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
         const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
-        if (nqc > k2::BLOCK_Q && k2_use_pair(force_pair)) {
+        if (nqc > k2::BLOCK_Q && !rowmap && k2_use_pair(force_pair)) {
             // CTA pairs (cta_group::2): 256-row tiles, CTA r of a pair owns queries [128r, 128r+128)
             const int tiles2 = (int)((n_rows + 255) / 256);
             int n_pairs = sm_count / 2;
@@ -491,10 +527,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (sampled) {
             if (QB == 2)
                 K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, st));
+                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, rowmap, st));
             else
                 K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, st));
+                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, rowmap, st));
             k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0, 1);
             K2CK(cudaGetLastError());
             *launches += 2;
@@ -505,10 +541,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
         if (QB == 2)
             K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, st));
+                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, rowmap, st));
         else
             K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, st));
+                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, rowmap, st));
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
         const int gridB = grid;
         K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,

@@ -19,7 +19,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               const float* q_sqnorm, const float* row_sqnorm,
               uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st, int* launches, std::string& err,
               cudaEvent_t ev_start = nullptr, cudaEvent_t ev_stop = nullptr,  // recorded around the main GEMM launch
-              bool force_pair = false);  // 129..256-query chunks on the cta_group::2 kernel
+              bool force_pair = false,  // 129..256-query chunks on the cta_group::2 kernel
+              // row-subset mode: `rows` is the whole matrix of matrix_rows rows, n_rows counts the entries of
+              // rowmap (padded to a multiple of 128 with valid rows); returned keys carry compact indices
+              const uint32_t* rowmap = nullptr, int64_t matrix_rows = 0);
 
 // pair kernel (k2_pair.cu)
 }  // namespace yrb

@@ -69,6 +69,16 @@ __device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMa
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
         : "memory");
 }
+// tile::gather4 — four rows of the 2-D tensor (row coordinates r0..r3, same column c0) land as four consecutive
+// box rows in shared memory: lets the GEMM read an arbitrary row subset (the rows passing a filter) in place
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2,
+                                            int r3) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -111,6 +111,13 @@ __global__ void __launch_bounds__(256) compact_gather_kernel(const uint4* __rest
     }
 }
 
+// row-subset mode of K2 (TMA gather4): only the squared norms are gathered, the rows are read in place
+__global__ void __launch_bounds__(256) compact_sqnorm_kernel(const float* __restrict__ sqnorm, const uint32_t* __restrict__ rowmap,
+                                                             int64_t n_out, float* __restrict__ out_sqnorm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) out_sqnorm[i] = sqnorm[rowmap[i]];
+}
+
 // keys / ids produced on the compact matrix → original row numbers
 __global__ void __launch_bounds__(256) compact_remap_kernel(const uint32_t* __restrict__ rowmap, int64_t n, uint64_t* __restrict__ keys,
                                                             int64_t* __restrict__ ids) {
@@ -143,6 +150,10 @@ cudaError_t launch_compact_gather(const uint32_t* mask, int64_t n_rows, const ui
     const int64_t n_words = (n_rows + 31) / 32;
     const int nb = (int)compact_scratch_words(n_rows);
     compact_map_kernel<<<nb, 256, 0, st>>>(mask, n_words, block_off, rowmap);
+    if (n_out > 0 && !out_rows) {  // map + norms only
+        compact_sqnorm_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(sqnorm, rowmap, n_out, out_sqnorm);
+        return cudaGetLastError();
+    }
     if (n_out > 0)
         compact_gather_kernel<<<sm_count * 8, 256, 0, st>>>(reinterpret_cast<const uint4*>(rows), sqnorm, rowmap, n_out, ld16,
                                                             reinterpret_cast<uint4*>(out_rows), out_sqnorm);
