@@ -43,6 +43,8 @@ WORKLOADS = {
     "c4b": (10_000_000, 1024, 256, 10, 0.10),
     "c5": (100_000_000, 768, 1024, 10, None),
     "tiny": (250_000, 1024, 1, 10, None),
+    "t10mb": (10_000_000, 1024, 256, 100, None),   # 256-query batches over the 10M corpus (near-linear scaling case)
+    "c3s": (125_000, 1024, 256, 100, None),        # one C3 shard of an 8-GPU run, for the fixed-cost breakdown
 }
 N_QUERY_SETS = 64
 

@@ -309,25 +309,39 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
 // thr0[q] = k-th largest of the (n_cta * m) published best scores: every one is the score of a distinct
 // real row, so at least k rows score >= thr0[q] and thr0[q] <= the true k-th best.  Fewer than k → -inf.
 // cta_stride 1: every CTA published for every query; 2 (pair kernel): CTA 2i + (q >= 128) published for q.
+// One warp per query: the k-th largest of the n = n_cta*m published scores by bisection on their monotone bit
+// patterns (32 rounds of compare + warp popcount) — no shared memory, no block barriers.
 __global__ void __launch_bounds__(256) k2_threshold_kernel(const float* __restrict__ tops, int n_cta, int m, int k,
-                                                           float* __restrict__ thr0, int cta_stride) {
-    __shared__ float sv[512];
-    const int q = blockIdx.x;
-    const int n = n_cta * m;
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
-        float v = -INFINITY;
+                                                           float* __restrict__ thr0, int cta_stride, int nq) {
+    const int lane = threadIdx.x & 31;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    const int n = n_cta * m;          // <= 2 * 148 + 32
+    uint32_t v[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const int i = lane + 32 * j;
+        float f = -INFINITY;
         if (i < n) {
             const int cta = (i / m) * cta_stride + (cta_stride == 2 && q >= BLOCK_Q ? 1 : 0);
-            v = tops[((int64_t)cta * MAX_TOPS + (i % m)) * MAX_Q + q];
+            f = tops[((int64_t)cta * MAX_TOPS + (i % m)) * MAX_Q + q];
         }
-        sv[i] = v;
+        v[j] = score_bits(f);
     }
-    block_bitonic_desc(sv, 512, [](float a, float b) { return a > b; });
-    if (threadIdx.x == 0) {
-        float t = (n >= k) ? sv[k - 1] : -INFINITY;
-        // one ulp below the k-th published score: rows tying with it still pass the strict `s > thr`
-        thr0[q] = nextafterf(t, -INFINITY);
+    uint32_t t = 0;
+    if (n >= k) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = t | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) c += (lane + 32 * j < n) && (v[j] >= cand);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(YRB_FULL, c, o);
+            if (c >= k) t = cand;
+        }
     }
+    // one ulp below the k-th published score: rows tying with it still pass the strict `s > thr`
+    if (lane == 0) thr0[q] = (n >= k) ? nextafterf(bits_score(t), -INFINITY) : -INFINITY;
 }
 
 }  // namespace k2
@@ -491,7 +505,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             if (sampled2) {
                 K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, 1, nqc, k, mask, mask_q_stride, nullptr, s->cand_keys,
                                       s->cand_cnt, s->tops, m_tops2, qn, xn, st));
-                k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, n_pairs, m_tops2, k, s->thr0, 2);
+                k2::k2_threshold_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(s->tops, n_pairs, m_tops2, k, s->thr0, 2, nqc);
                 K2CK(cudaGetLastError());
                 *launches += 2;
                 thr2 = s->thr0;
@@ -531,7 +545,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             else
                 K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
                                     s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, rowmap, st));
-            k2::k2_threshold_kernel<<<nqc, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0, 1);
+            k2::k2_threshold_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0, 1, nqc);
             K2CK(cudaGetLastError());
             *launches += 2;
             thr = s->thr0;
