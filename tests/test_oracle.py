@@ -88,3 +88,31 @@ def test_faiss_flat_restatement_matches_exact():
     ref_ids, ref_s = ox.exact_topk(x, q, 10, "euclidean")
     assert np.array_equal(ids, ref_ids)
     np.testing.assert_allclose(sim, 1.0 / (1.0 + (1.0 - ref_s)), rtol=1e-5)   # faiss_store.py:181-182
+
+
+def test_c_restatement_agrees_with_numpy_oracle():
+    """Third independent statement of the path (plain C, oracle/exact_search.c) vs the numpy oracle."""
+    from oracle import c_oracle
+
+    rng = np.random.default_rng(12)
+    x = unit_rows(4000, 96, 13) * rng.uniform(0.5, 2.0, (4000, 1)).astype(np.float32)
+    x[[10, 3000]] = x[10]
+    x[77] = 0
+    assert np.array_equal(c_oracle.normalize(x).view(np.uint32), ox.l2_normalize(x).view(np.uint32))
+    sample = rng.standard_normal(2000).astype(np.float32) * 10.0 ** rng.integers(-6, 6, 2000)
+    assert np.array_equal(c_oracle.bf16_bits(sample), ox.bf16_bits(sample))
+    mask = rng.random(4000) < 0.3
+    mask[[10, 3000]] = True
+    for metric in ("cosine", "dot", "euclidean"):
+        for dtype in ("bf16", "f32"):
+            rows = ox.prepare(x, metric, dtype)
+            stored = ox.bf16_bits(rows) if dtype == "bf16" else rows
+            for q in (x[10], unit_rows(1, 96, 14)[0] * 1.7):
+                qp = ox.prepare(q, metric, dtype)[0]
+                for m in (None, mask):
+                    want_ids, want_s = ox.exact_topk(rows, qp, 25, metric, m)
+                    got_ids, got_s = c_oracle.topk(stored, qp, 25, metric, None if m is None else ox.pack_mask(m))
+                    assert np.array_equal(got_ids, want_ids), (metric, dtype)
+                    np.testing.assert_allclose(got_s, want_s, rtol=1e-12, atol=1e-12)
+    ids, _ = c_oracle.topk(ox.bf16_bits(ox.prepare(x[:3], "cosine", "bf16")), ox.prepare(x[0], "cosine", "bf16")[0], 10, "cosine")
+    assert ids.shape[0] == 3

@@ -70,7 +70,6 @@ struct yrb_index {
     float* d_qsq = nullptr;
     uint64_t* d_parts = nullptr;
     uint64_t* d_keys = nullptr;
-    uint64_t* d_mscratch = nullptr;
     unsigned char* d_result = nullptr;  // [ids nq*k i64 | scores nq*k f32 | counts nq i32], one D2H
     size_t result_bytes = 0;
     int64_t* d_ids = nullptr;           // views into d_result for the current (nq, k)
@@ -160,7 +159,6 @@ int ensure_capacity(yrb_index* ix, int64_t want) {
         c.present_host.resize(mask_words(cap), 0u);
     }
     ix->capacity = cap;
-    if (ix->k2) yrb::k2_invalidate(ix->k2);
     return YRB_OK;
 }
 
@@ -191,7 +189,6 @@ void free_scratch(yrb_index* ix) {
     FREE_DEV(ix->d_qsq);
     FREE_DEV(ix->d_parts);
     FREE_DEV(ix->d_keys);
-    FREE_DEV(ix->d_mscratch);
     FREE_DEV(ix->d_result);
     ix->d_ids = nullptr;
     ix->d_scores = nullptr;
@@ -214,7 +211,6 @@ int ensure_scratch(yrb_index* ix, int nq, int k) {
     CK(cudaMalloc(&ix->d_qsq, (size_t)nqc * 4));
     CK(cudaMalloc(&ix->d_parts, (size_t)parts * nqc * kc * 8));
     CK(cudaMalloc(&ix->d_keys, (size_t)nqc * kc * 8));
-    CK(cudaMalloc(&ix->d_mscratch, (size_t)parts * nqc * kc * 8));
     ix->result_bytes = (size_t)nqc * kc * 12 + (size_t)nqc * 4;
     CK(cudaMalloc(&ix->d_result, ix->result_bytes));
     CK(cudaMallocHost(&ix->h_q, (size_t)nqc * ix->dim * 4));

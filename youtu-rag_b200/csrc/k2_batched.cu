@@ -370,7 +370,6 @@ void k2_destroy(K2State* s) {
     if (s->thr0) cudaFree(s->thr0);
     delete s;
 }
-void k2_invalidate(K2State*) {}
 int k2_parts(int sm_count) { return sm_count; }
 bool k2_supported(int dtype, int dim, int k) { return dtype == 0 && dim >= 1 && k >= 1 && k <= YRB_FUSED_K_MAX; }
 

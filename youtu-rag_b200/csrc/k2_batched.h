@@ -7,10 +7,9 @@
 
 namespace yrb {
 
-struct K2State;  // cached TMA descriptors + candidate buffers of one index
+struct K2State;  // driver entry point for tensor-map encoding + candidate buffers of one index
 K2State* k2_create();
 void k2_destroy(K2State* s);
-void k2_invalidate(K2State* s);  // corpus pointer / capacity changed
 int k2_parts(int sm_count);      // sorted k-lists K2 leaves per query before K3
 bool k2_supported(int dtype, int dim, int k);
 // q: prepared bf16 queries [nq, ld].  Writes nq*k keys (descending) to out_keys.  Returns YRB_* code.

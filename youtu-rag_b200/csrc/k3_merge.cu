@@ -1,63 +1,16 @@
-// K3 — top-k merge: P sorted k-lists per query → one sorted k-list.  Used (a) to merge the
-// per-CTA lists of K1/K2 on one GPU and (b) as the local step of the cross-GPU merge collective
-// after the NCCL all-gather (no reference counterpart — the reference is one
-// Chroma collection in one process, chroma_store.py:41-59).
+// K3 (merge form) — the local step of the cross-GPU merge after the NCCL all-gather (the baseline
+// exchange; K7 in k7_exchange.cu does transfer + merge in one kernel), and the key decoder of the K6 path.
+// SURVEY.md §8e; no reference counterpart — the reference is one Chroma collection in one process,
+// chroma_store.py:41-59.  Per-GPU selection over unsorted candidates lives in k3_select.cu / select.cuh.
 //
-// One CTA per (query, group of lists): candidates are loaded into shared memory, sorted with a
-// block bitonic network on 64-bit keys (score desc, row asc) and the first k written back.
-// Work is KiB-scale and latency-bound; bytes are negligible next to the scan.
+// One CTA per query: world*k candidates are loaded into shared memory, sorted with a block bitonic
+// network on (score desc, GLOBAL id asc) and the first k written back.  KiB-scale, latency-bound.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace yrb {
 
 constexpr int MERGE_THREADS = 512;
-constexpr int MERGE_CAP = 4096;  // keys per CTA pass (32 KiB shared)
-
-// in: [parts][nq][k]; CTA (q, grp) merges lists [grp*G, min(parts,(grp+1)*G)) → out[grp][q][k]
-__global__ void __launch_bounds__(MERGE_THREADS)
-    merge_keys_kernel(const uint64_t* __restrict__ in, int parts, int nq, int k, int G, uint64_t* __restrict__ out) {
-    __shared__ uint64_t sk[MERGE_CAP];
-    const int q = blockIdx.x, grp = blockIdx.y;
-    const int p0 = grp * G;
-    const int np = min(G, parts - p0);
-    const int n = np * k;
-    const int npow = next_pow2(n);
-    for (int i = threadIdx.x; i < npow; i += blockDim.x) {
-        uint64_t v = 0;
-        if (i < n) {
-            const int p = p0 + i / k, j = i - (i / k) * k;
-            v = in[((int64_t)p * nq + q) * k + j];
-        }
-        sk[i] = v;
-    }
-    block_bitonic_desc(sk, npow, BetterU64());
-    for (int i = threadIdx.x; i < k; i += blockDim.x) out[((int64_t)grp * nq + q) * k + i] = (i < n) ? sk[i] : 0ull;
-}
-
-cudaError_t launch_merge_keys(const uint64_t* in, int parts, int nq, int k, uint64_t* out, uint64_t* scratch,
-                              cudaStream_t st) {
-    if (k > MERGE_CAP / 2) return cudaErrorInvalidValue;
-    const int G = MERGE_CAP / k;
-    const uint64_t* cur = in;
-    int p = parts;
-    // ping-pong inside scratch: pass outputs are at most ceil(p/G) lists
-    uint64_t* bufs[2] = {scratch, scratch ? scratch + (int64_t)((parts + G - 1) / G) * nq * k : nullptr};
-    int flip = 0;
-    while (true) {
-        const int groups = (p + G - 1) / G;
-        uint64_t* dst = (groups == 1) ? out : bufs[flip];
-        if (groups > 1 && !scratch) return cudaErrorInvalidValue;
-        merge_keys_kernel<<<dim3(nq, groups), MERGE_THREADS, 0, st>>>(cur, p, nq, k, G, dst);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        if (groups == 1) break;
-        cur = dst;
-        p = groups;
-        flip ^= 1;
-    }
-    return cudaSuccess;
-}
 
 __global__ void decode_kernel(const uint64_t* __restrict__ keys, int nq, int k, int64_t* __restrict__ ids,
                               float* __restrict__ scores, int32_t* __restrict__ counts) {

@@ -40,10 +40,7 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
                       unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st);
 
-// ---- K3: merge `parts` sorted k-lists per query ([parts][nq][k]) into [nq][k] (descending keys).
-// scratch must hold parts*nq*k keys when parts*k > 4096 (multi-pass).
-cudaError_t launch_merge_keys(const uint64_t* in, int parts, int nq, int k, uint64_t* out,
-                              uint64_t* scratch, cudaStream_t st);
+// ---- K3: selection / merge
 // sorted top-k of unsorted candidates gathered from n_seg segments per query (see k3_select.cu):
 // key pointer of (seg, q) = base + seg*seg_stride + q*q_stride; its length = counts[seg*cnt_seg_stride +
 // q*cnt_q_stride] (or fixed_cnt), clamped to seg_cap; zero keys are skipped; thr (optional) keeps
