@@ -76,6 +76,7 @@ struct yrb_index {
     float* d_scores = nullptr;
     int32_t* d_counts = nullptr;
     unsigned int* d_ticket = nullptr;   // K1's last-CTA-done counter
+    unsigned long long* d_k1trace = nullptr;  // YRB_K1_TRACE=1: per-CTA phase stamps of the last K1 launch
     // K8 compaction scratch (grow-only)
     uint32_t* d_cp_blocks = nullptr;
     size_t cp_blocks_cap = 0;
@@ -510,12 +511,48 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             yrb::K1Out o{out_keys + (size_t)j * k, ids ? ids + (size_t)j * k : nullptr,
                          scores ? scores + (size_t)j * k : nullptr, counts ? counts + j : nullptr};
             bool fused = false;
+            static const bool trace = getenv("YRB_K1_TRACE") != nullptr;
+            if (trace) {
+                if (!ix->d_k1trace) CK(cudaMalloc(&ix->d_k1trace, (size_t)256 * 8 * 8));
+                CK(cudaMemsetAsync(ix->d_k1trace, 0, (size_t)256 * 8 * 8, st));
+                o.trace = ix->d_k1trace;
+            }
             int rc = prof_mark(ix, st);
             if (rc) return rc;
             CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
                               ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, k, pk, ix->d_ticket, o, &fused, sms, st));
             if ((rc = prof_mark(ix, st))) return rc;
             ix->launches++;
+            if (trace) {  // debug aid: phase breakdown of this launch on stderr (µs relative to the first CTA's start)
+                std::vector<unsigned long long> h((size_t)(parts + 2) * 8);
+                CK(cudaStreamSynchronize(st));
+                CK(cudaMemcpy(h.data(), ix->d_k1trace, h.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long t0 = ~0ull;
+                for (int c = 0; c < parts; ++c) t0 = std::min(t0, h[(size_t)c * 8]);
+                const char* names[8] = {"start", "prep_done", "scan_done", "cta_merge_done", "ticket_done", "final_done", "warp0_scan_done", "first_group_done"};
+                for (int ph = 0; ph < 8; ++ph) {
+                    double lo = 1e30, hi = -1e30, sum = 0;
+                    int n = 0;
+                    for (int c = 0; c < parts; ++c) {
+                        const unsigned long long t = h[(size_t)c * 8 + ph];
+                        if (!t) continue;
+                        const double us = (double)(t - t0) * 1e-3;
+                        lo = std::min(lo, us);
+                        hi = std::max(hi, us);
+                        sum += us;
+                        ++n;
+                    }
+                    if (n) fprintf(stderr, "[k1trace] %-16s n=%3d min %8.2f avg %8.2f max %8.2f us\n", names[ph], n, lo, sum / n, hi);
+                }
+                const unsigned long long* f = h.data() + (size_t)parts * 8;  // the last CTA's final merge
+                const unsigned long long* c0 = f + 8;  // CTA 0's own merge
+                if (c0[0])
+                    fprintf(stderr, "[k1trace] cta0 merge:  begin %.2f init %.2f bound %.2f ranked %.2f (survivors %llu) emitted %.2f us\n",
+                            (c0[0] - t0) * 1e-3, (c0[1] - t0) * 1e-3, (c0[2] - t0) * 1e-3, (c0[3] - t0) * 1e-3, c0[6], (c0[4] - t0) * 1e-3);
+                if (f[0])
+                    fprintf(stderr, "[k1trace] final merge: begin %.2f staged %.2f bound %.2f ranked %.2f (survivors %llu) emitted %.2f us\n",
+                            (f[0] - t0) * 1e-3, (f[1] - t0) * 1e-3, (f[2] - t0) * 1e-3, (f[3] - t0) * 1e-3, f[6], (f[4] - t0) * 1e-3);
+            }
             if (!fused) {
                 CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, parts, k, k, nullptr, 1, k, o.final_keys, st, o.ids,
                                                o.scores, o.count));
@@ -654,6 +691,7 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_DEV(ix->d_prog);
     FREE_DEV(ix->d_pass);
     FREE_DEV(ix->d_ticket);
+    FREE_DEV(ix->d_k1trace);
     FREE_DEV(ix->d_progs);
     FREE_HOST(ix->h_progs);
     FREE_DEV(ix->d_qmasks);

@@ -13,6 +13,7 @@
 // Algorithmic bytes per search: sel·N·ld·esize + N/8 (mask) + ld·esize (query) + parts·k·8.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -27,6 +28,16 @@ constexpr int K1_R = 4;   // rows per batch
 constexpr int K1_CU = 4;  // chunks per unrolled step
 
 int k1_parts(int sm_count) { return sm_count; }
+
+__device__ __forceinline__ unsigned long long k1_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define K1_STAMP(i)                                                                  \
+    do {                                                                             \
+        if (out.trace && threadIdx.x == 0) out.trace[blockIdx.x * 8 + (i)] = k1_now(); \
+    } while (0)
 
 template <bool F32>
 __device__ __forceinline__ float dot_chunk(uint4 v, float4 qa, float4 qb, float acc) {
@@ -82,16 +93,48 @@ __device__ __forceinline__ float prepare_query(const float* __restrict__ q_raw, 
         }
         sqn = warp_sum(sqn);
     }
-    for (int i = threadIdx.x; i < nch * 32; i += blockDim.x) {
-        const int c = i >> 5, l = i & 31;
-        const int e0 = i * EPL;
-        float v[EPL];
+    // one float4 (4 elements) per thread: the fp64 divides are spread over the whole CTA
+    for (int i = threadIdx.x; i < nch * 32 * H; i += blockDim.x) {
+        const int item = i / H, h = i - item * H;  // item = chunk * 32 + lane
+        const int c = item >> 5, l = item & 31;
+        const int e0 = item * EPL + h * 4;
+        float v[4];
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) v[j] = (e0 + j < ld) ? stored(e0 + j) : 0.f;
-        sq[(c * H) * 32 + l] = make_float4(v[0], v[1], v[2], v[3]);
-        if (!F32) sq[(c * H + 1) * 32 + l] = make_float4(v[4], v[5], v[6], v[7]);
+        for (int j = 0; j < 4; ++j) v[j] = (e0 + j < ld) ? stored(e0 + j) : 0.f;
+        sq[(c * H + h) * 32 + l] = make_float4(v[0], v[1], v[2], v[3]);
     }
     return sqn;
+}
+
+// one unrolled step of K1_R rows x K1_CU chunks: the loads …
+__device__ __forceinline__ void rows_load_step(const uint4* const (&rp)[K1_R], const bool (&va)[K1_R], int ld16, int c0,
+                                               int lane, uint4 (&v)[K1_R][K1_CU]) {
+#pragma unroll
+    for (int cc = 0; cc < K1_CU; ++cc) {
+        const int off = (c0 + cc) * 32 + lane;
+        const bool in = off < ld16;
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) {
+            v[r][cc] = make_uint4(0, 0, 0, 0);
+            if (in && va[r]) v[r][cc] = ldg_stream(rp[r] + off);
+        }
+    }
+}
+// … and the multiply-adds against the staged query
+template <bool F32>
+__device__ __forceinline__ void rows_fma_step(const uint4 (&v)[K1_R][K1_CU], int c0, int nch, const float4* sq, int lane,
+                                              float (&acc)[K1_R]) {
+    constexpr int H = F32 ? 1 : 2;
+#pragma unroll
+    for (int cc = 0; cc < K1_CU; ++cc) {
+        const int c = c0 + cc;
+        if (c < nch) {
+            const float4 qa = sq[(c * H) * 32 + lane];
+            const float4 qb = F32 ? qa : sq[(c * H + 1) * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < K1_R; ++r) acc[r] = dot_chunk<F32>(v[r][cc], qa, qb, acc[r]);
+        }
+    }
 }
 
 // dot products of K1_R rows (row pointers rp[], warp-uniform validity va[]) with the staged query;
@@ -99,35 +142,118 @@ __device__ __forceinline__ float prepare_query(const float* __restrict__ q_raw, 
 template <bool F32>
 __device__ __forceinline__ void rows_dot(const uint4* const (&rp)[K1_R], const bool (&va)[K1_R], int ld16, int nch,
                                          const float4* sq, int lane, float (&acc)[K1_R]) {
-    constexpr int H = F32 ? 1 : 2;
 #pragma unroll
     for (int r = 0; r < K1_R; ++r) acc[r] = 0.f;
     for (int c0 = 0; c0 < nch; c0 += K1_CU) {
         uint4 v[K1_R][K1_CU];
-#pragma unroll
-        for (int cc = 0; cc < K1_CU; ++cc) {
-            const int off = (c0 + cc) * 32 + lane;
-            const bool in = off < ld16;
-#pragma unroll
-            for (int r = 0; r < K1_R; ++r) {
-                v[r][cc] = make_uint4(0, 0, 0, 0);
-                if (in && va[r]) v[r][cc] = ldg_stream(rp[r] + off);
-            }
-        }
-#pragma unroll
-        for (int cc = 0; cc < K1_CU; ++cc) {
-            const int c = c0 + cc;
-            if (c < nch) {
-                const float4 qa = sq[(c * H) * 32 + lane];
-                const float4 qb = F32 ? qa : sq[(c * H + 1) * 32 + lane];
-#pragma unroll
-                for (int r = 0; r < K1_R; ++r) acc[r] = dot_chunk<F32>(v[r][cc], qa, qb, acc[r]);
-            }
-        }
+        rows_load_step(rp, va, ld16, c0, lane, v);
+        rows_fma_step<F32>(v, c0, nch, sq, lane, acc);
     }
 #pragma unroll
     for (int r = 0; r < K1_R; ++r) acc[r] = warp_sum(acc[r]);
 }
+
+// Exact top-k of `n_lists` (<= 256) descending-sorted, 0-padded key lists in shared memory (list l at
+// sk[l*stride .. +k)), k <= 32, by pruning + ranking instead of a serial k-step tournament.  No atomics, every
+// step spread over the whole CTA:
+//   1. bound: with depth = ceil(k / n_lists) and m = ceil(k / depth), the m-th largest of the lists' depth-th
+//      entries (T) has at least m*depth >= k keys at or above it.  The entries are ranked by counting, each
+//      entry's comparisons split over up to 4 threads.  Keys are unique, so the ranks are a permutation.
+//   2. n_lists >= k (depth 1): only the <= k lists whose head reaches T can hold a result; list of rank r is
+//      copied to row r of a k x k matrix M, so step 3 scans k*k keys instead of n_lists*k.  Otherwise
+//      (n_lists < k) the lists themselves are the rows.  Rows are sorted: a row's survivors (keys >= T) are a prefix.
+//   3. a prefix sum over the rows' survivor counts numbers the survivors; warp w takes survivors w, w+16, …, and
+//      counts the keys above each one (lanes over the matrix, redux): that count is its output slot.
+// Called by every thread of the CTA; emit(slot, key) runs exactly once per slot in [0, k) (key 0 = empty).
+struct MergeScratch {
+    unsigned long long T;
+    int hot[32];                     // list holding the r-th largest head (step 2), -1 = none
+    int cnt[32];                     // survivors per row
+    unsigned short partial[4][256];  // partial ranks of step 1
+};
+template <class Emit>
+__device__ __forceinline__ int merge_sorted_lists(const uint64_t* sk, int n_lists, int stride, int k, uint64_t* M,
+                                                  MergeScratch* ms, Emit emit, unsigned long long* dbg = nullptr) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int depth = (k + n_lists - 1) / n_lists;
+    const int m = (k + depth - 1) / depth;
+    const int d1 = depth - 1;
+    const bool copy = depth == 1;
+    int P = nt / n_lists;
+    P = P > 4 ? 4 : (P < 1 ? 1 : P);
+    const int chunk = (n_lists + P - 1) / P;
+    if (tid == 0) ms->T = 0ull;
+    if (tid < 32) {
+        ms->hot[tid] = -1;
+        ms->cnt[tid] = 0;
+    }
+    __syncthreads();
+    if (dbg && tid == 0) dbg[1] = k1_now();
+    for (int t = tid; t < n_lists * P; t += nt) {  // 1a. thread (entry i, part p): comparisons against one slice
+        const int p = t / n_lists, i = t - p * n_lists;
+        const uint64_t h = sk[i * stride + d1];
+        const int j1 = (p + 1) * chunk < n_lists ? (p + 1) * chunk : n_lists;
+        int c = 0;
+        for (int j = p * chunk; j < j1; ++j) c += sk[j * stride + d1] > h;
+        ms->partial[p][i] = (unsigned short)c;
+    }
+    __syncthreads();
+    for (int i = tid; i < n_lists; i += nt) {  // 1b. ranks; the bound; the lists that can reach it
+        const uint64_t h = sk[i * stride + d1];
+        if (h != 0ull) {
+            int c = 0;
+            for (int p = 0; p < P; ++p) c += ms->partial[p][i];
+            if (c < m) {
+                if (c == m - 1) ms->T = h;
+                if (copy) ms->hot[c] = i;
+            }
+        }
+    }
+    __syncthreads();
+    if (dbg && tid == 0) dbg[2] = k1_now();
+    const uint64_t T = ms->T;
+    const uint64_t* src = copy ? M : sk;
+    const int rows = copy ? k : n_lists, rstride = copy ? k : stride;  // rows <= 32 either way
+    for (int r = warp; r < rows; r += nw) {  // 2. rows and their survivor counts
+        uint64_t mine = 0ull;
+        if (copy) {
+            const int l = ms->hot[r];
+            if (l >= 0 && lane < k) mine = sk[l * stride + lane];
+            if (lane < k) M[r * k + lane] = mine;
+        } else if (lane < k) {
+            mine = sk[r * stride + lane];
+        }
+        const unsigned int live = __ballot_sync(YRB_FULL, mine != 0ull && mine >= T);
+        if (lane == 0) ms->cnt[r] = __popc(live);
+    }
+    __syncthreads();
+    if (dbg && tid == 0) dbg[3] = k1_now();
+    const int myc = lane < rows ? ms->cnt[lane] : 0;
+    int incl = myc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(YRB_FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int ns = __shfl_sync(YRB_FULL, incl, 31);
+    const int span = rows * rstride;
+    for (int sv = warp; sv < ns; sv += nw) {  // 3. survivor sv: row = number of rows that end at or before it
+        const int r = __popc(__ballot_sync(YRB_FULL, incl <= sv));
+        const int excl = __shfl_sync(YRB_FULL, incl - myc, r);
+        const uint64_t key = src[r * rstride + (sv - excl)];
+        int c = 0;
+        for (int j = lane; j < span; j += 32) c += src[j] > key;
+        c = __reduce_add_sync(YRB_FULL, c);
+        if (lane == 0 && c < k) emit(c, key);
+    }
+    for (int r = ns + tid; r < k; r += nt) emit(r, 0ull);
+    if (dbg && tid == 0) {
+        dbg[4] = k1_now();
+        dbg[6] = (unsigned long long)ns;
+    }
+    return ns < k ? ns : k;
+}
+constexpr int K1_RANK_K = 32;  // largest k merged by ranking
 
 template <bool F32, int KPL, bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
@@ -139,24 +265,20 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    K1_STAMP(0);
 
+    const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
+    const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
     const float q_sqn = prepare_query<F32>(q_raw, dim, ld, nch, normalize, l2 != 0, sq);
     __syncthreads();
+    K1_STAMP(1);
     const float l2_bias = l2 ? (1.f - q_sqn) : 0.f;
 
     WarpList<KPL> list;
     list.clear();
     uint64_t thr = 0;
 
-    const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
-    const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
-
-    auto consume = [&](const int64_t (&rid)[K1_R], const bool (&va)[K1_R]) {
-        const uint4* rp[K1_R];
-#pragma unroll
-        for (int r = 0; r < K1_R; ++r) rp[r] = rows + rid[r] * (int64_t)ld16;
-        float acc[K1_R];
-        rows_dot<F32>(rp, va, ld16, nch, sq, lane, acc);
+    auto offer = [&](const int64_t (&rid)[K1_R], const bool (&va)[K1_R], const float (&acc)[K1_R]) {
 #pragma unroll
         for (int r = 0; r < K1_R; ++r) {
             if (va[r]) {
@@ -170,6 +292,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             }
         }
     };
+    auto consume = [&](const int64_t (&rid)[K1_R], const bool (&va)[K1_R]) {
+        const uint4* rp[K1_R];
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) rp[r] = rows + rid[r] * (int64_t)ld16;
+        float acc[K1_R];
+        rows_dot<F32>(rp, va, ld16, nch, sq, lane, acc);
+        offer(rid, va, acc);
+    };
 
     // Masked scans hand out 64-row mask groups dynamically (first group = the warp's global index, further
     // ones from an atomic counter): the number of passing rows per group varies, so static dealing would
@@ -179,11 +309,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     auto grab_issue = [&]() -> unsigned int { return lane == 0 ? atomicAdd(ticket + 1, 1u) : 0u; };
     auto grab_get = [&](unsigned int c) -> int64_t { return (int64_t)__shfl_sync(YRB_FULL, c, 0) + tw; };
     if (!HAS_MASK) {
-        // dense: groups of K1_R rows dealt round-robin to all warps of the grid.  Every warp then sweeps the
-        // same moving window of the matrix (best DRAM locality) and the tail imbalance is one 4-row group;
-        // measured 8-20 % faster than 64-row dynamic chunks, whose quantisation costs more than it saves.
+        // dense: groups of K1_R rows dealt round-robin to all warps of the grid, so every warp sweeps the same
+        // moving window of the matrix (best DRAM locality; 64-row dynamic chunks measured 8-20 % slower, their
+        // quantisation costs more than it saves).  SMs do not all get the same share of the bandwidth, though
+        // (CTAs of a 125k-row scan finished between 37 and 45 us), so the last eighth of the groups is handed
+        // out by tickets of two groups.  A warp draws its first ticket at kernel start and the next one before it
+        // consumes the current one, so the atomic's round trip is never waited for.  (Measured alternatives, all
+        // slower: tickets drawn late, one-group tickets — more same-address atomics in the tail —, and requesting
+        // the first group's rows before the query is prepared, which delays the query's own loads.)
         const int64_t n_groups4 = (n_rows + K1_R - 1) / K1_R;
-        for (int64_t g = gw; g < n_groups4; g += tw) {
+        const int64_t n_static = (n_groups4 - n_groups4 / 8) / tw * tw;  // whole sweeps
+        unsigned int nx = grab_issue();
+        auto do_group = [&](int64_t g) {
             int64_t rid[K1_R];
             bool va[K1_R];
 #pragma unroll
@@ -193,6 +330,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 if (!va[r]) rid[r] = 0;
             }
             consume(rid, va);
+        };
+        for (int64_t g = gw; g < n_static; g += tw) {
+            do_group(g);
+            if (out.trace && g == gw && threadIdx.x == 0) out.trace[blockIdx.x * 8 + 7] = k1_now();  // first group done
+        }
+        for (;;) {
+            const int64_t g = n_static + 2 * (int64_t)__shfl_sync(YRB_FULL, nx, 0);
+            if (g >= n_groups4) break;
+            nx = grab_issue();
+            do_group(g);
+            if (g + 1 < n_groups4) do_group(g + 1);
         }
     } else {
         // Passing rows are queued across 64-row mask groups so that every batch carries K1_R rows:
@@ -235,7 +383,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     }
 
     // ---- CTA merge: every warp's first k entries → shared → tournament → first k to global
+    if (out.trace && lane == 0 && warp == 0) out.trace[blockIdx.x * 8 + 6] = k1_now();  // warp 0 left the scan
     __syncthreads();  // query no longer needed; shared memory is reused for keys
+    K1_STAMP(2);
     uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
     const int kp = next_pow2(k);  // ≤ 32*KPL
 #pragma unroll
@@ -244,10 +394,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         if (e < kp) sk[warp * kp + e] = (e < k) ? list.v[s] : 0ull;
     }
     __syncthreads();
-    // The 16 per-warp lists are each sorted: warp 0 merges them with a k-step tournament (lane l < 16 holds the
-    // head of list l, a butterfly max picks the winner, whose lane advances) — a fraction of a microsecond,
-    // against ~36 block-wide barriers for a bitonic sort of the same keys.
-    if (warp == 0) {
+    if constexpr (KPL == 1) {
+        // k <= 32: prune + rank over the 16 sorted per-warp lists, all threads (see merge_sorted_lists)
+        uint64_t* M = sk + K1_WARPS * kp;  // k*k <= 16*kp keys when the lists are copied (k <= 16)
+        MergeScratch* ms = reinterpret_cast<MergeScratch*>(M + K1_WARPS * kp);
+        uint64_t* dst = part_keys + (int64_t)blockIdx.x * k;
+        unsigned long long* dbg = (out.trace && blockIdx.x == 0) ? out.trace + (size_t)(gridDim.x + 1) * 8 : nullptr;
+        if (dbg && threadIdx.x == 0) dbg[0] = k1_now();
+        merge_sorted_lists(sk, K1_WARPS, kp, k, M, ms, [&](int slot, uint64_t key) { dst[slot] = key; }, dbg);
+    } else if (warp == 0) {
+        // k > 32: warp 0 merges the lists with a k-step tournament (lane l < 16 holds the head of list l, a
+        // butterfly max picks the winner, whose lane advances)
         int pos = 0;
         uint64_t head = (lane < K1_WARPS) ? sk[lane * kp] : 0ull;
         for (int i = 0; i < k; ++i) {
@@ -268,63 +425,40 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     // ---- fused K3: the last CTA to arrive merges all per-CTA lists (no second launch)
     {
         __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
+        __syncthreads();  // the CTA's part_keys stores are issued
+        K1_STAMP(3);
         if (threadIdx.x == 0) {
+            __threadfence();  // cumulative over the barrier: publishes every thread's stores before the ticket
             const unsigned int t = atomicAdd(ticket, 1u);
             s_last = (t == gridDim.x - 1);
             if (s_last) {
                 ticket[0] = 0u;  // every CTA has left the scan: rearm both counters for the next launch
                 ticket[1] = 0u;
+                __threadfence();
             }
         }
         __syncthreads();
+        K1_STAMP(4);
         if (s_last && fuse_stage > 0) {
-            __threadfence();
             SelectArgs a{part_keys, k, 0, nullptr, 0, 0, (int)gridDim.x, k, k, nullptr, k, out.final_keys,
                          out.ids, out.scores, out.count};
             const int parts = (int)gridDim.x;
-            if (k <= 32 && parts <= 256) {
-                // small k: the per-CTA lists are sorted, so stage them (one parallel round of L2 reads) and let
-                // warp 0 run a k-step tournament over the list heads (lane l owns lists l, l+32, …).
+            if (KPL == 1 && parts <= 256) {
+                // k <= 32: stage the sorted per-CTA lists (one parallel round of L2 reads), then prune + rank
+                unsigned long long* dbg = out.trace ? out.trace + (size_t)gridDim.x * 8 : nullptr;
+                if (dbg && threadIdx.x == 0) dbg[0] = k1_now();
                 for (int i = threadIdx.x; i < parts * k; i += blockDim.x) sk[i] = __ldcg(part_keys + i);
-                __syncthreads();
-                if (warp == 0) {
-                    int pos[8];
-                    uint64_t head[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        pos[j] = 0;
-                        const int l = lane + 32 * j;
-                        head[j] = l < parts ? sk[l * k] : 0ull;
-                    }
-                    int n_out = 0;
-                    for (int i = 0; i < k; ++i) {
-                        uint64_t best = head[0];
-#pragma unroll
-                        for (int j = 1; j < 8; ++j) best = head[j] > best ? head[j] : best;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const uint64_t other = shfl_xor_u64(best, o);
-                            best = other > best ? other : best;
-                        }
-                        if (lane == 0) select_emit(a, 0, i, best);
-                        n_out += best != 0ull;
-                        if (best != 0ull) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (head[j] == best) {   // unique keys: exactly one (lane, j) matches
-                                    ++pos[j];
-                                    head[j] = pos[j] < k ? sk[(lane + 32 * j) * k + pos[j]] : 0ull;
-                                }
-                        }
-                    }
-                    if (lane == 0 && a.out_counts) a.out_counts[0] = n_out;
-                }
+                uint64_t* M = sk + parts * k;
+                MergeScratch* ms = reinterpret_cast<MergeScratch*>(M + K1_RANK_K * K1_RANK_K);
+                const int n_out =
+                    merge_sorted_lists(sk, parts, k, k, M, ms, [&](int slot, uint64_t key) { select_emit(a, 0, slot, key); }, dbg);
+                if (threadIdx.x == 0 && a.out_counts) a.out_counts[0] = n_out;
             } else {
                 SelectScratch& S = *reinterpret_cast<SelectScratch*>(smem_raw + (size_t)fuse_stage * 8);
                 select_topk_block(a, 0, sk, fuse_stage, S);
             }
+            __syncthreads();
+            K1_STAMP(5);
         }
     }
 }
@@ -374,8 +508,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 
 static size_t k1_smem_bytes(int dtype, int nch, int k, int fuse_stage) {
     size_t q = (size_t)nch * 32 * (dtype == 1 ? 1 : 2) * sizeof(float4);
-    size_t m = (size_t)K1_WARPS * next_pow2(k) * sizeof(uint64_t);
+    size_t m = (size_t)K1_WARPS * next_pow2(k) * sizeof(uint64_t) * 2 + sizeof(MergeScratch);  // lists + survivors
     size_t f = fuse_stage > 0 ? select_smem_bytes(fuse_stage) : 0;
+    if (fuse_stage > 0 && k <= K1_RANK_K)  // staged lists + k x k matrix + scratch of the ranking merge
+        f = std::max(f, (size_t)fuse_stage * 8 + (size_t)K1_RANK_K * K1_RANK_K * 8 + sizeof(MergeScratch));
     size_t r = q > m ? q : m;
     return r > f ? r : f;
 }

@@ -35,6 +35,7 @@ struct K1Out {
     int64_t* ids;          // optional [k]
     float* scores;         // optional [k]
     int32_t* count;        // optional [1]
+    unsigned long long* trace = nullptr;  // optional [grid][8] phase stamps (globaltimer ns), YRB_K1_TRACE
 };
 cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,

@@ -14,6 +14,8 @@ tensors and the merge runs through `merge_host`, a test-only stand-in for K3.
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -55,7 +57,8 @@ class ShardedSearcher:
             self.stream = torch.cuda.Stream(self.device)
             self.comm_stream = torch.cuda.Stream(self.device, priority=-1) if self.world > 1 else self.stream
             if self.world > 1:
-                index.set_reserved_sms(2)   # room for the exchange kernel beside the persistent scan
+                # room for the exchange kernel beside the persistent scan (YRB_RESERVED_SMS overrides, for experiments)
+                index.set_reserved_sms(int(os.environ.get("YRB_RESERVED_SMS", "2")))
         self._bufs = {}
         self._hq = {}
         # exchange: "p2p" = K7, one kernel storing into peers' buffers over NVLink (CUDA IPC); "nccl" = all-gather
