@@ -41,7 +41,8 @@ struct SelectScratch {
     uint64_t sel[SEL_KMAX];
     uint64_t red[SEL_THREADS / 32 * 2];
     int seg_cnt[SEL_MAX_SEG];
-    int s_n, s_nsel, s_bstar, s_above;
+    int seg_off[SEL_MAX_SEG + 1];  // exclusive prefix of seg_cnt (dense staging)
+    int s_n, s_nsel, s_bstar, s_above, s_zero;
 };
 __host__ __device__ constexpr size_t select_smem_bytes(int stage_keys) {
     return (size_t)stage_keys * 8 + sizeof(SelectScratch);
@@ -65,11 +66,75 @@ __device__ __forceinline__ void select_topk_block(const SelectArgs& a, const int
     __syncthreads();
 
     // ---- stage (filtered) candidates; count them even when they do not fit.
-    // Four threads share a segment so that all segment reads are in flight together (the loop is
-    // latency-bound: segments are short and live in L2).
     for (int seg = tid; seg < a.n_seg; seg += SEL_THREADS) S.seg_cnt[seg] = seg_count(a, seg, q);
+    if (tid == 0) S.s_zero = 0;
     __syncthreads();
-    for (int seg0 = 0; seg0 < a.n_seg; seg0 += SEL_THREADS / 4) {
+    bool staged = false;
+    if (a.thr == nullptr) {
+        // Dense staging: a prefix sum over the segment lengths numbers the candidates, thread t takes candidates
+        // t, t+512, … (segment by binary search in the prefix), four loads in flight per thread.  The loop below
+        // this one walks each segment with a ballot/atomic per step — one L2 round trip per step, ~28 of them
+        // for C3's ~5600 candidates in 148 segments — and is kept for filtered selections.
+        if (warp == 0) {
+            int loc[SEL_MAX_SEG / 32], sum = 0;
+#pragma unroll
+            for (int j = 0; j < SEL_MAX_SEG / 32; ++j) {
+                const int sg = lane * (SEL_MAX_SEG / 32) + j;
+                loc[j] = sg < a.n_seg ? S.seg_cnt[sg] : 0;
+                sum += loc[j];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(YRB_FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < SEL_MAX_SEG / 32; ++j) {
+                S.seg_off[lane * (SEL_MAX_SEG / 32) + j] = run;
+                run += loc[j];
+            }
+            if (lane == 31) S.seg_off[SEL_MAX_SEG] = incl;
+        }
+        __syncthreads();
+        const int total = S.seg_off[SEL_MAX_SEG];
+        if (total <= stage) {
+            const uint64_t* qbase = a.base + (int64_t)q * a.q_stride;
+            bool zero = false;
+            for (int i0 = tid; i0 < total; i0 += 4 * SEL_THREADS) {
+                uint64_t key[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * SEL_THREADS;
+                    key[u] = 1ull;
+                    if (i < total) {
+                        int lo = 0, hi = SEL_MAX_SEG - 1;  // largest sg with seg_off[sg] <= i (empty segments share offsets)
+#pragma unroll
+                        for (int step = 0; step < 8; ++step) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (S.seg_off[mid] <= i) lo = mid; else hi = mid - 1;
+                        }
+                        key[u] = qbase[(int64_t)lo * a.seg_stride + (i - S.seg_off[lo])];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * SEL_THREADS;
+                    if (i < total) sk[i] = key[u];
+                    zero |= key[u] == 0ull;
+                }
+            }
+            if (zero) S.s_zero = 1;  // an empty key inside a segment: recount with the compacting loop
+            if (tid == 0) s_n = total;
+            __syncthreads();
+            staged = S.s_zero == 0;
+            if (!staged && tid == 0) s_n = 0;
+            __syncthreads();
+        }
+    }
+    // Compacting staging: four threads share a segment so that all segment reads are in flight together.
+    for (int seg0 = 0; !staged && seg0 < a.n_seg; seg0 += SEL_THREADS / 4) {
         const int seg = seg0 + (tid >> 2), r = tid & 3;
         const int c = seg < a.n_seg ? S.seg_cnt[seg] : 0;
         const uint64_t* src = a.base + (int64_t)seg * a.seg_stride + (int64_t)q * a.q_stride;
