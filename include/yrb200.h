@@ -155,7 +155,9 @@ YRB_API int yrb_index_search_multi(yrb_index* ix, const float* queries, int nq, 
 
 /* All-device variant for resident inputs (bench `value`, sharded search): queries fp32 [nq, dim]
  * on the device, mask device words or NULL, outputs = nq*k packed 64-bit selection keys
- * (see yrb_key_*), best first, 0 = empty slot.  Asynchronous on `stream`. */
+ * (see yrb_key_*), best first, 0 = empty slot.  Asynchronous on `stream`.
+ * All searches of one index share its scratch (per-CTA lists, ticket counters, candidate buffers):
+ * enqueue them on ONE stream, or order streams with events; concurrent searches need separate indexes. */
 YRB_API int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k,
                             const uint32_t* dev_mask, uint64_t* dev_out_keys, void* stream);
 
