@@ -71,6 +71,7 @@ struct yrb_index {
     uint64_t* d_parts = nullptr;
     uint64_t* d_keys = nullptr;
     unsigned char* d_result = nullptr;  // [ids nq*k i64 | scores nq*k f32 | counts nq i32], one D2H
+    unsigned char* d_result_host = nullptr;  // device alias of h_result (pinned, mapped): small results are written there
     size_t result_bytes = 0;
     int64_t* d_ids = nullptr;           // views into d_result for the current (nq, k)
     float* d_scores = nullptr;
@@ -196,6 +197,7 @@ void free_scratch(yrb_index* ix) {
     ix->d_counts = nullptr;
     FREE_HOST(ix->h_q);
     FREE_HOST(ix->h_result);
+    ix->d_result_host = nullptr;
     ix->nq_cap = ix->k_cap = 0;
 }
 
@@ -216,18 +218,29 @@ int ensure_scratch(yrb_index* ix, int nq, int k) {
     CK(cudaMalloc(&ix->d_result, ix->result_bytes));
     CK(cudaMallocHost(&ix->h_q, (size_t)nqc * ix->dim * 4));
     CK(cudaMallocHost(&ix->h_result, ix->result_bytes));
+    {
+        void* alias = nullptr;  // pinned memory is device-accessible under unified addressing; no alias → D2H copies only
+        if (cudaHostGetDevicePointer(&alias, ix->h_result, 0) != cudaSuccess) {
+            cudaGetLastError();
+            alias = nullptr;
+        }
+        ix->d_result_host = static_cast<unsigned char*>(alias);
+    }
     ix->nq_cap = nqc;
     ix->k_cap = kc;
     return YRB_OK;
 }
 
 // carve d_result for this call's (nq, k): ids | scores | counts, contiguous → one D2H copy
-size_t result_views(yrb_index* ix, int nq, int k) {
-    ix->d_ids = reinterpret_cast<int64_t*>(ix->d_result);
-    ix->d_scores = reinterpret_cast<float*>(ix->d_result + (size_t)nq * k * 8);
-    ix->d_counts = reinterpret_cast<int32_t*>(ix->d_result + (size_t)nq * k * 12);
+// `base`: d_result, or the device alias of the pinned host buffer (results of a few hundred bytes are stored
+// straight to host memory by the selecting kernel: no copy-engine round trip after the scan)
+size_t result_views(yrb_index* ix, int nq, int k, unsigned char* base) {
+    ix->d_ids = reinterpret_cast<int64_t*>(base);
+    ix->d_scores = reinterpret_cast<float*>(base + (size_t)nq * k * 8);
+    ix->d_counts = reinterpret_cast<int32_t*>(base + (size_t)nq * k * 12);
     return (size_t)nq * k * 12 + (size_t)nq * 4;
 }
+constexpr size_t ZERO_COPY_RESULT_MAX = 4096;
 
 // upload the host mirror of a bitmask range [w0, w1)
 int upload_words(uint32_t* dev, const std::vector<uint32_t>& host, int64_t w0, int64_t w1, cudaStream_t st) {
@@ -982,7 +995,12 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     cudaStream_t st = ix->stream;
     memcpy(ix->h_q, queries, (size_t)nq * ix->dim * 4);
     CK(cudaMemcpyAsync(ix->d_qf32, ix->h_q, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, st));
-    const size_t res_bytes = result_views(ix, nq, ke);
+    static const bool zc_enabled = [] {
+        const char* e = getenv("YRB_ZERO_COPY");  // "0" keeps the D2H copy (A/B measurements)
+        return !(e && e[0] == '0');
+    }();
+    const bool zero_copy = zc_enabled && ix->d_result_host && (size_t)nq * ke * 12 + (size_t)nq * 4 <= ZERO_COPY_RESULT_MAX;
+    const size_t res_bytes = result_views(ix, nq, ke, zero_copy ? ix->d_result_host : ix->d_result);
     const uint32_t* dev_extra = nullptr;
     if (mask) {
         uint32_t* d_user = ix->d_usermask;
@@ -1009,7 +1027,7 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     }
     if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, m_stride, ix->d_keys, ix->d_ids, ix->d_scores, ix->d_counts, st);
     if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = zero_copy ? cudaSuccess : cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = fail(YRB_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
     } else {
