@@ -28,6 +28,14 @@ import threading
 import time
 from pathlib import Path
 
+if "reference" in sys.argv and int(os.environ.get("RANK", "0")) == 0:
+    # torchrun pins OMP_NUM_THREADS=1 for multi-rank launches; the reference arm is a CPU measurement on rank 0
+    # alone and must use every host core it can, as it does when launched without torchrun (BLAS reads these
+    # variables when numpy is imported, hence before the import)
+    _cores = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = _cores
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
