@@ -315,11 +315,17 @@ def run_b200(args):
     for i in range(max(3, args.warmup // 4)):
         step_host(i)
     barrier()
+    host_lat = []
     t0 = time.perf_counter()
+    t_prev = t0
     for i in range(e2e_steps):
         step_host(i)
+        t_now = time.perf_counter()
+        host_lat.append(t_now - t_prev)  # host call -> ids/scores on the host (SURVEY.md §8d's latency)
+        t_prev = t_now
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    host_lat.sort()
     t = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -378,6 +384,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * dim * 4,
                     "d2h_bytes_per_step": nq * k * 12 + nq * 4, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                    "p50_ms": 1e3 * host_lat[len(host_lat) // 2], "p99_ms": 1e3 * host_lat[min(len(host_lat) - 1, int(len(host_lat) * 0.99))],
                     "steps": e2e_steps, "api": "yrb_index_search (C ABI, host buffers)" if world == 1 and dev_mask is None
                     else "ShardedSearcher.search (host buffers)"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "exchange": searcher.exchange_kind,
