@@ -218,3 +218,51 @@ def test_k2_compaction_for_selective_shared_mask(sel, metric):
     c = int(counts2[0])
     check_topk(ids2[0, :c], scores2[0, :c], rows, ox.prepare(qs[0], metric, "bf16")[0], k, metric, "bf16", mask=m2,
                tie_eps=2e-5 if metric == "euclidean" else None)
+
+
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+@pytest.mark.parametrize("nq", [2, 4, 5, 9])
+def test_k1q_fp32_batches_match_oracle_and_the_k1_loop(metric, nq):
+    """fp32 storage: batches go through K1Q (four queries per pass over the rows).  Same per-row arithmetic as
+    K1, so ids AND score bits must equal a K1 loop; both must match the oracle."""
+    n, d = 30011, 1024 if nq == 4 else 200
+    x = unit_rows(n, d, 41) * np.random.default_rng(42).uniform(0.5, 1.5, (n, 1)).astype(np.float32)
+    x[[5, 7000, 29999]] = x[5]                       # ties broken by row id
+    ix = native.Index(d, metric, "f32", 0, 0)
+    ix.append(x)
+    rows = ix.read_rows(np.arange(n))
+    qs = unit_rows(nq, d, 43) * 1.2
+    qs[0] = x[5]
+    mask = np.random.default_rng(44).random(n) < 0.3
+    mask[[5, 7000, 29999]] = True
+    for k in (1, 10, 32):
+        for m in (None, mask):
+            pm = None if m is None else ox.pack_mask(m)
+            ids, scores, counts = ix.search(qs, k, mask=pm)              # auto path → K1Q
+            ix.set_path(native.PATH_K1)
+            ids1, scores1, counts1 = ix.search(qs, k, mask=pm)           # forced: one K1 scan per query
+            ix.set_path(native.PATH_AUTO)
+            assert np.array_equal(ids, ids1) and np.array_equal(counts, counts1)
+            if metric == "euclidean":   # ||q||^2 comes from K5 here and from K1's fused prologue there
+                np.testing.assert_allclose(scores, scores1, rtol=0, atol=1e-6)
+            else:
+                assert np.array_equal(scores.view(np.uint32), scores1.view(np.uint32))
+            for j in range(nq):
+                c = int(counts[j])
+                assert c == k
+                check_topk(ids[j, :c], scores[j, :c], rows, ox.prepare(qs[j], metric, "f32")[0], k, metric, "f32", mask=m,
+                           tie_eps=2e-5 if metric == "euclidean" else None)
+    if metric == "cosine":
+        assert ids[0, :3].tolist() == [5, 7000, 29999]
+
+
+def test_k1q_fewer_passing_rows_than_k():
+    n, d = 5000, 64
+    x = unit_rows(n, d, 45)
+    ix = native.Index(d, "cosine", "f32", 0, 0)
+    ix.append(x)
+    mask = np.zeros(n, bool)
+    mask[[3, 77, 4999]] = True
+    ids, scores, counts = ix.search(unit_rows(6, d, 46), 10, mask=ox.pack_mask(mask))
+    assert counts.tolist() == [3] * 6
+    assert all(sorted(ids[j, :3].tolist()) == [3, 77, 4999] and (ids[j, 3:] == -1).all() for j in range(6))

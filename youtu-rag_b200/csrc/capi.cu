@@ -517,6 +517,22 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         }
         return rc;
     }
+    if (path == 1 && ix->path == 0 && ix->dtype == 1 && nq >= 2 && k <= yrb::K1Q_MAX_K && mask_q_stride == 0) {
+        // K1Q: fp32-storage batches share each pass over the rows between four queries (K2 is bf16-only)
+        const int parts = yrb::k1_parts(sms);
+        CK(yrb::launch_ingest(dev_q, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
+        ix->launches++;
+        for (int c0 = 0; c0 < nq; c0 += yrb::K1Q_MAX_Q) {
+            const int n = std::min(yrb::K1Q_MAX_Q, nq - c0);
+            CK(yrb::launch_k1q_f32(ix->d_rows, ix->rows, ix->ld, reinterpret_cast<const float*>(ix->d_q) + (size_t)c0 * ix->ld, n,
+                                   ix->d_qsq + c0, ix->d_sqnorm, ix->metric, mask, k, ix->d_parts, sms, st));
+            CK(yrb::launch_select_segments(ix->d_parts, k, (int64_t)parts * k, nullptr, 0, 0, parts, k, k, nullptr, n, k,
+                                           out_keys + (size_t)c0 * k, st, ids ? ids + (size_t)c0 * k : nullptr,
+                                           scores ? scores + (size_t)c0 * k : nullptr, counts ? counts + c0 : nullptr));
+            ix->launches += 2;
+        }
+        return YRB_OK;
+    }
     if (path == 1) {
         const int parts = yrb::k1_parts(sms);
         for (int j = 0; j < nq; ++j) {

@@ -463,6 +463,146 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
     }
 }
 
+// ---- K1Q: fp32-storage batches.  K2 is a bf16 tensor-core kernel; on an fp32 index a batch used to loop K1, one
+// scan of the matrix per query.  Here K1Q_NQ = 4 queries share each pass: a row is loaded once and multiplied
+// into four accumulators (fp32 rows need one FMA per element and no unpacking, so four queries still leave the
+// scan HBM-bound: 16 FMAs per 16 loaded bytes ≈ 20 % of the FMA pipe at the full stream rate).  Same
+// per-row arithmetic and summation order as K1, so scores are bit-identical to the single-query path.
+// Queries arrive prepared (K5: normalised fp32 rows [nq][ld] + their squared norms); one shared mask; k <= 32.
+// Per-CTA lists are merged per query with merge_sorted_lists; the cross-CTA selection is K3's launch.
+constexpr int K1Q_NQ = 4;
+constexpr int K1Q_CU = 2;  // chunks per unrolled step (4 rows x 2 chunks = 8 loads in flight per lane)
+
+template <bool HAS_MASK>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+    k1q_scan_f32(const uint4* __restrict__ rows, int64_t n_rows, int ld16, int nch, const float4* __restrict__ q_prep,
+                 int nq, const float* __restrict__ q_sqn, const float* __restrict__ row_sqnorm, int l2,
+                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ part_keys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* sq = reinterpret_cast<float4*>(smem_raw);  // [K1Q_NQ][nch*32] float4, zero for missing queries / padding
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < K1Q_NQ * nch * 32; i += blockDim.x) {
+        const int qi = i / (nch * 32), c = i - qi * (nch * 32);
+        sq[i] = (qi < nq && c < ld16) ? q_prep[(int64_t)qi * ld16 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float l2_bias[K1Q_NQ];
+#pragma unroll
+    for (int qi = 0; qi < K1Q_NQ; ++qi) l2_bias[qi] = (l2 && qi < nq) ? 1.f - q_sqn[qi] : 0.f;
+    __syncthreads();
+
+    WarpList<1> list[K1Q_NQ];
+    uint64_t thr[K1Q_NQ];
+#pragma unroll
+    for (int qi = 0; qi < K1Q_NQ; ++qi) {
+        list[qi].clear();
+        thr[qi] = 0ull;
+    }
+    const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
+    const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
+    const int64_t n_groups4 = (n_rows + K1_R - 1) / K1_R;
+    for (int64_t g = gw; g < n_groups4; g += tw) {
+        int64_t rid[K1_R];
+        bool va[K1_R];
+        bool any = false;
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) {
+            rid[r] = g * K1_R + r;
+            va[r] = rid[r] < n_rows;
+            if (va[r] && HAS_MASK) va[r] = (mask[rid[r] >> 5] >> (rid[r] & 31)) & 1u;
+            if (!va[r]) rid[r] = 0;
+            any |= va[r];
+        }
+        if (!any) continue;  // warp-uniform
+        float acc[K1_R][K1Q_NQ];
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r)
+#pragma unroll
+            for (int qi = 0; qi < K1Q_NQ; ++qi) acc[r][qi] = 0.f;
+        for (int c0 = 0; c0 < nch; c0 += K1Q_CU) {
+            uint4 v[K1_R][K1Q_CU];
+#pragma unroll
+            for (int cc = 0; cc < K1Q_CU; ++cc) {
+                const int off = (c0 + cc) * 32 + lane;
+                const bool in = off < ld16;
+#pragma unroll
+                for (int r = 0; r < K1_R; ++r) {
+                    v[r][cc] = make_uint4(0, 0, 0, 0);
+                    if (in && va[r]) v[r][cc] = ldg_stream(rows + rid[r] * (int64_t)ld16 + off);
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < K1Q_CU; ++cc) {
+                const int c = c0 + cc;
+                if (c < nch) {
+#pragma unroll
+                    for (int qi = 0; qi < K1Q_NQ; ++qi) {
+                        const float4 qa = sq[(qi * nch + c) * 32 + lane];
+#pragma unroll
+                        for (int r = 0; r < K1_R; ++r) acc[r][qi] = dot_chunk<true>(v[r][cc], qa, qa, acc[r][qi]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < K1_R; ++r) {
+            const float xs = (l2 && va[r]) ? row_sqnorm[rid[r]] : 0.f;
+#pragma unroll
+            for (int qi = 0; qi < K1Q_NQ; ++qi) {
+                float sc = warp_sum(acc[r][qi]);
+                if (va[r] && qi < nq) {
+                    if (l2) sc = fmaf(2.f, sc, l2_bias[qi] - xs);
+                    const uint64_t key = make_key(sc, (uint32_t)rid[r]);
+                    if (key > thr[qi]) {
+                        list[qi].insert(key, lane);
+                        thr[qi] = list[qi].at(k - 1);
+                    }
+                }
+            }
+        }
+    }
+
+    // per-CTA merge, one query after the other (the query tiles in shared memory are no longer needed)
+    __syncthreads();
+    uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);
+    const int kp = next_pow2(k);
+    uint64_t* M = sk + K1_WARPS * kp;
+    MergeScratch* ms = reinterpret_cast<MergeScratch*>(M + K1_WARPS * kp);
+#pragma unroll
+    for (int qi = 0; qi < K1Q_NQ; ++qi) {
+        if (qi < nq) {  // CTA-uniform
+            if (lane < kp) sk[warp * kp + lane] = (lane < k) ? list[qi].v[0] : 0ull;
+            __syncthreads();
+            uint64_t* dst = part_keys + ((int64_t)qi * gridDim.x + blockIdx.x) * k;
+            merge_sorted_lists(sk, K1_WARPS, kp, k, M, ms, [&](int slot, uint64_t key) { dst[slot] = key; });
+            __syncthreads();
+        }
+    }
+}
+
+cudaError_t launch_k1q_f32(const void* rows, int64_t n_rows, int ld, const float* q_prep, int nq, const float* q_sqn,
+                           const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
+                           int sm_count, cudaStream_t st) {
+    if (nq < 1 || nq > K1Q_NQ || k < 1 || k > K1_RANK_K) return cudaErrorInvalidValue;
+    const int ld16 = ld * 4 / 16;
+    const int nch = (ld16 + 31) / 32;
+    const size_t q_bytes = (size_t)K1Q_NQ * nch * 32 * sizeof(float4);
+    const size_t m_bytes = (size_t)K1_WARPS * next_pow2(k) * sizeof(uint64_t) * 2 + sizeof(MergeScratch);
+    const size_t smem = std::max(q_bytes, m_bytes);
+    const int l2 = (metric == 2);
+    const int grid = k1_parts(sm_count);
+    auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, K1_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(rows), n_rows, ld16, nch,
+                                             reinterpret_cast<const float4*>(q_prep), nq, q_sqn, row_sqnorm, l2, mask, k, part_keys);
+        return cudaGetLastError();
+    };
+    return mask ? launch(k1q_scan_f32<true>) : launch(k1q_scan_f32<false>);
+}
+
 // ---- K6a: plain scores (any k): score of every row for one query; masked-out rows get key-0
 // semantics downstream by writing -inf-like NaN pattern?  No: they are written as -INFINITY and
 // the select step also receives the mask.

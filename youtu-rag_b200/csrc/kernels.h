@@ -41,6 +41,14 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
                       unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st);
 
+// K1Q: up to 4 prepared fp32 queries ([nq][ld] fp32 + squared norms, from launch_ingest) against fp32 rows in one
+// pass; one shared mask; k <= 32.  Writes per-CTA sorted lists part_keys[q][cta][k]; finish with
+// launch_select_segments(part_keys, k, parts*k, nullptr, 0, 0, parts, k, k, nullptr, nq, k, …).
+constexpr int K1Q_MAX_Q = 4, K1Q_MAX_K = 32;
+cudaError_t launch_k1q_f32(const void* rows, int64_t n_rows, int ld, const float* q_prep, int nq, const float* q_sqn,
+                           const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
+                           int sm_count, cudaStream_t st);
+
 // ---- K3: selection / merge
 // sorted top-k of unsorted candidates gathered from n_seg segments per query (see k3_select.cu):
 // key pointer of (seg, q) = base + seg*seg_stride + q*q_stride; its length = counts[seg*cnt_seg_stride +
