@@ -127,7 +127,7 @@ def test_batched_euclidean(dtype):
     ix.append(x)
     rows = ix.read_rows(np.arange(n))
     qs = unit_rows(nq, d, 33)
-    ids, scores, counts = ix.search(qs, 10)          # bf16 → K2 with the euclidean epilogue; f32 → K1 loop
+    ids, scores, counts = ix.search(qs, 10)          # bf16 → K2 with the euclidean epilogue; f32 → K1Q
     for j in (0, 17, 39):
         check_topk(ids[j], scores[j], rows, ox.prepare(qs[j], "euclidean", dtype)[0], 10, "euclidean", dtype, tie_eps=2e-5)
 
