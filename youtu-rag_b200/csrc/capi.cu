@@ -525,12 +525,13 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         for (int c0 = 0; c0 < nq; c0 += yrb::K1Q_MAX_Q) {
             const int n = std::min(yrb::K1Q_MAX_Q, nq - c0);
             CK(yrb::launch_k1q_f32(ix->d_rows, ix->rows, ix->ld, reinterpret_cast<const float*>(ix->d_q) + (size_t)c0 * ix->ld, n,
-                                   ix->d_qsq + c0, ix->d_sqnorm, ix->metric, mask, k, ix->d_parts, sms, st));
-            CK(yrb::launch_select_segments(ix->d_parts, k, (int64_t)parts * k, nullptr, 0, 0, parts, k, k, nullptr, n, k,
-                                           out_keys + (size_t)c0 * k, st, ids ? ids + (size_t)c0 * k : nullptr,
-                                           scores ? scores + (size_t)c0 * k : nullptr, counts ? counts + c0 : nullptr));
-            ix->launches += 2;
+                                   ix->d_qsq + c0, ix->d_sqnorm, ix->metric, mask, k, ix->d_parts + (size_t)c0 * parts * k, sms, st));
+            ix->launches++;
         }
+        // one selection launch for the whole batch: query q's per-CTA lists sit at d_parts[q][cta][k]
+        CK(yrb::launch_select_segments(ix->d_parts, k, (int64_t)parts * k, nullptr, 0, 0, parts, k, k, nullptr, nq, k, out_keys, st,
+                                       ids, scores, counts));
+        ix->launches++;
         return YRB_OK;
     }
     if (path == 1) {

@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 // Queries arrive prepared (K5: normalised fp32 rows [nq][ld] + their squared norms); one shared mask; k <= 32.
 // Per-CTA lists are merged per query with merge_sorted_lists; the cross-CTA selection is K3's launch.
 constexpr int K1Q_NQ = 4;
-constexpr int K1Q_CU = 2;  // chunks per unrolled step (4 rows x 2 chunks = 8 loads in flight per lane)
+constexpr int K1Q_CU = 4;  // chunks per unrolled step (4 rows x 4 chunks = 16 loads in flight per lane, as K1)
 
 template <bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
