@@ -9,7 +9,10 @@
 // loads in flight per lane); the query lives in shared memory as fp32; a row's score is a
 // warp butterfly sum; each warp keeps a sorted top-k of 64-bit keys spread over its lanes and
 // only touches it when a score beats the current k-th key.  Rows failing the bitmask are never
-// loaded.  Per-CTA lists are merged with a block bitonic sort; K3 merges the CTAs.
+// loaded.  The 16 per-warp lists of a CTA, and then the per-CTA lists in the last CTA to finish, are merged
+// by pruning + ranking (merge_sorted_lists, k <= 32) or a tournament + K3's block selection (k <= 128), so a
+// whole search is one launch.  K1Q (further down) shares a pass between four fp32 queries; k6_scores writes
+// the plain key vector for the any-k path.
 // Algorithmic bytes per search: sel·N·ld·esize + N/8 (mask) + ld·esize (query) + parts·k·8.
 #include <cuda_bf16.h>
 
