@@ -92,3 +92,38 @@ def test_context_assembler_reproduces_reference():
     dup = hits[:3] + [RetrievalResult(chunk=hits[1].chunk, score=0.99, rank=1)]
     merged = merge_results(dup)
     assert [(r.chunk.id, r.score) for r in merged] == [("c0", 1.0), ("c1", 0.99), ("c2", hits[2].score)]
+
+
+def test_filters_emitted_by_the_reference_toolkits_compile_and_evaluate():
+    """the `where` dicts produced by the reference's own toolkit code (captured unmodified by
+    tests/golden/make_filter_golden.py) pass the product's validator, compile to a K4 program, and that
+    program — interpreted on the CPU — selects the rows the oracle selects."""
+    import json
+    from pathlib import Path
+
+    import numpy as np
+
+    from oracle import where_eval as ow
+    from tests.test_where_host import interpret
+    from youtu_rag_b200.metadata import MetadataTable
+    from youtu_rag_b200.where import compile_where, normalize_filters, validate_where
+
+    g = json.loads((Path(__file__).parent / "golden" / "filter_producers.json").read_text())
+    metas = g["metadatas"]
+    table = MetadataTable()
+    table.append(metas)
+    seen = 0
+    for case in g["cases"]:
+        where = case["where"]
+        if where is None:
+            assert case["rows"] is None
+            continue
+        validate_where(where)
+        assert normalize_filters(where) == where          # toolkit output is already in operator form: passed verbatim
+        want = np.zeros(len(metas), bool)
+        want[case["rows"]] = True
+        assert np.array_equal(ow.eval_where(where, metas), want), case["producer"]
+        prog, _cols = compile_where(where, table)
+        assert np.array_equal(interpret(prog, table), want), (case["producer"], where)
+        seen += 1
+    assert seen >= 13

@@ -99,3 +99,31 @@ def test_where_then_search_is_prefilter():
     from tests.helpers import check_topk
     check_topk(ids[0, :counts[0]], scores[0, :counts[0]], ix.read_rows(np.arange(n)), ox.prepare(q, "cosine", "bf16")[0], 10,
                "cosine", "bf16", mask=mask)
+
+
+def test_where_from_reference_filter_producers():
+    """K4 on the `where` dicts the reference's toolkits emit (tests/golden/filter_producers.json),
+    and a filtered search with each of them against the oracle."""
+    from pathlib import Path
+
+    from tests.helpers import check_topk
+
+    g = json.loads((Path(__file__).parent / "golden" / "filter_producers.json").read_text())
+    metas = g["metadatas"]
+    ix, t = _setup(metas, d=32)
+    rows = ix.read_rows(np.arange(ix.rows))
+    q = unit_rows(1, 32, 5)[0]
+    qp = ox.prepare(q, "cosine", "bf16")[0]
+    for case in g["cases"]:
+        if case["where"] is None:
+            continue
+        want = np.zeros(len(metas), bool)
+        want[case["rows"]] = True
+        assert np.array_equal(_mask(ix, t, case["where"]), want), case["producer"]
+        prog, cols = compile_where(case["where"], t)
+        t.sync(ix, cols)
+        ids, scores, counts = ix.search(q, 5, where=prog)
+        c = int(counts[0])
+        assert c == min(5, int(want.sum()))
+        if c:
+            check_topk(ids[0, :c], scores[0, :c], rows, qp, 5, "cosine", "bf16", mask=want)
