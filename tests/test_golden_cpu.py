@@ -127,3 +127,50 @@ def test_filters_emitted_by_the_reference_toolkits_compile_and_evaluate():
         assert np.array_equal(interpret(prog, table), want), (case["producer"], where)
         seen += 1
     assert seen >= 13
+
+
+def test_memory_and_skill_rescoring_matches_the_reference_toolkit():
+    """rank_memories / rank_skills against VectorMemoryToolkit.search_memories / search_skills run
+    unmodified over preset hits (tests/golden/make_memory_golden.py): same order, same relevance."""
+    import json
+    from datetime import datetime
+    from pathlib import Path
+
+    from youtu_rag_b200 import Chunk, rank_memories, rank_skills
+
+    g = json.loads((Path(__file__).parent / "golden" / "memory_rescoring.json").read_text())
+    now = datetime.fromisoformat(g["now"])
+
+    def chunks(hits):
+        return [(Chunk(id=h["id"], document_id="d", content=h["document"], chunk_index=0, metadata=dict(h["metadata"])),
+                 1.0 - h["distance"]) for h in hits]
+
+    import numpy as np
+
+    from oracle import where_eval as ow
+    from tests.test_where_host import interpret
+    from youtu_rag_b200.metadata import MetadataTable
+    from youtu_rag_b200.where import compile_where, validate_where
+
+    for case in g["memories"]:
+        where = case["query"]["where"]          # shorthand leaves inside $and (memory_toolkit.py:880-894)
+        if where is not None:
+            metas = [h["metadata"] for h in g["memories"][0]["hits"]]
+            table = MetadataTable()
+            table.append(metas)
+            validate_where(where)
+            prog, _ = compile_where(where, table)
+            assert np.array_equal(interpret(prog, table), ow.eval_where(where, metas)), where
+        got = rank_memories(chunks(case["hits"]), now=now)
+        assert [c.id for c, _, _ in got] == [r["id"] for r in case["results"]], case["kwargs"]
+        for (c, sim, rel), r in zip(got, case["results"]):
+            assert abs(sim - (1.0 - r["distance"])) < 1e-12 and abs(rel - r["relevance"]) < 1e-12
+    for case in g["skills"]:
+        kw = case["kwargs"]
+        assert case["query"]["n_results"] == 2 * kw["top_k"] and case["query"]["where"] is None   # callers over-fetch 2k
+        tf = kw.get("tool_filter")
+        got = rank_skills(chunks(case["hits"]), top_k=kw["top_k"], min_success_rate=kw.get("min_success_rate", 0.3),
+                          tool_filter=[tf] if isinstance(tf, str) else tf, now=now)
+        assert [c.id for c, _, _ in got] == [r["id"] for r in case["results"]], kw
+        for (c, sim, rel), r in zip(got, case["results"]):
+            assert abs(rel - r["relevance"]) < 1e-12
