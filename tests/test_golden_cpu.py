@@ -174,3 +174,46 @@ def test_memory_and_skill_rescoring_matches_the_reference_toolkit():
         assert [c.id for c, _, _ in got] == [r["id"] for r in case["results"]], kw
         for (c, sim, rel), r in zip(got, case["results"]):
             assert abs(rel - r["relevance"]) < 1e-12
+
+
+def test_postprocessing_matches_the_reference_toolkits():
+    """per-file dedup of file-level search and the merge of several searches' hits, against
+    KBSearchToolkit.kb_file_search / MetaRetrievalToolkit.merge_retrieval_results run unmodified
+    (tests/golden/make_postprocess_golden.py); the filter kb_file_search composes must compile for K4."""
+    import json
+    from pathlib import Path
+
+    from youtu_rag_b200 import Chunk, RetrievalResult
+    from youtu_rag_b200.metadata import MetadataTable
+    from youtu_rag_b200.postprocess import dedup_by_file, merge_results
+    from youtu_rag_b200.where import compile_where, validate_where
+
+    g = json.loads((Path(__file__).parent / "golden" / "postprocess.json").read_text())
+
+    def rr(h):
+        return RetrievalResult(chunk=Chunk(id=h["id"], document_id=h["document_id"], content=h["content"],
+                                           chunk_index=h["chunk_index"], metadata=dict(h["metadata"])), score=h["score"], rank=h["rank"])
+
+    hits = [rr(h) for h in g["hits"]]
+    table = MetadataTable()
+    table.append([h["metadata"] for h in g["hits"]])
+    for case in g["file_search"]:
+        kw, want = case["kwargs"], case["output"]
+        top_k = kw["top_k"] if kw["top_k"] is not None else 4              # KBSelf.file_search_top_k in the generator
+        assert case["retriever_top_k"] == top_k                            # auto_rerank=False: no over-fetch
+        validate_where(case["filters"])                                     # {"$and": [base, {"index_type": {"$eq": "index_summary"}}]}
+        compile_where(case["filters"], table)
+        files = dedup_by_file(hits, include_summary=kw["include_summary"])
+        assert want["total_files"] == len(files)
+        shaped = []
+        for idx, e in enumerate(files[:top_k], 1):
+            x = {"rank": idx, "file_name": e["file_name"], "embedding_score": round(e["relevance_score"], 4), "metadata": e["metadata"]}
+            if kw["include_summary"]:
+                x["summary"] = e.get("summary", "")
+            shaped.append(x)
+        assert shaped == want["files"], kw
+    for case in g["merge"]:
+        got = merge_results([rr(h) for h in case["input"]])
+        want = case["output"]["results"]
+        assert [(r.chunk.id, r.rank, round(r.score, 4)) for r in got] == [(w["chunk_id"], w["rank"], w["similarity_score"]) for w in want]
+        assert [r.chunk.metadata for r in got] == [w["metadata"] for w in want]
