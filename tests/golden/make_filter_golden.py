@@ -5,6 +5,8 @@ The producer methods are taken UNMODIFIED (source text, via ast) from
   /root/reference/utu/rag/rag_tools/meta_retrieval_toolkit.py  MetaRetrievalToolkit._build_metadata_filters :102-186
                                                                MetaRetrievalToolkit._build_time_range_filter :188-255
   /root/reference/utu/rag/storage/implementations/memory_store.py  MemoryVectorStore.search_memories         :377-424
+  /root/reference/utu/rag/knowledge_retrieval/chroma_retrical_text2sql.py  CourseSearcher.search             :148-194
+      (called once per text column with the same question by unified_schemalink_valuelink.py:289-303)
 and executed here on representative arguments (the modules themselves do not import in this container: agents SDK,
 hydra, chromadb are missing, so the functions are exec'd in a bare namespace; `search_memories` is run with a stub
 `self` whose `search` records the filters it is handed).  The fixture pins the dicts; their evaluation over the
@@ -44,8 +46,11 @@ def method_source(path: Path, cls: str, name: str) -> str:
 
 
 def load(path: Path, cls: str, name: str):
-    ns = {"Optional": Optional, "Any": Any, "logger": logging.getLogger("ref")}
-    exec(method_source(path, cls, name), ns)  # noqa: S102 - reference source, executed unmodified
+    from typing import Dict, List
+
+    ns = {"Optional": Optional, "Any": Any, "List": List, "Dict": Dict, "logger": logging.getLogger("ref"),
+          "Chunk": object, "MemoryType": str}   # names that only appear in signatures
+    exec(compile(method_source(path, cls, name), str(path), "exec", dont_inherit=True), ns)  # noqa: S102 - unmodified
     return ns[name]
 
 
@@ -62,6 +67,8 @@ def sample_metadata(n=240, seed=3):
             m["创建时间_min_stamp"], m["创建时间_max_stamp"] = lo, lo + int(rng.integers(0, 40)) * 86_400
         if i % 3 == 0:
             m["author"], m["year"] = ["张三", "John"][i % 2], int(2018 + i % 8)
+        if i % 2:
+            m.update(type=["column_value", "table_schema"][i % 4 == 3], table_name=f"t{i % 3}", column_name=f"col{(i // 7) % 4}")
         if i % 5 == 0:
             m.update(session_id=f"s{i % 2}", memory_type=["episodic", "procedural"][(i // 10) % 2],
                      importance_score=float(rng.integers(0, 11)) / 10, success_rate=float(rng.integers(0, 11)) / 10)
@@ -115,6 +122,32 @@ def run():
         s = MemSelf()
         asyncio.run(mem_f(s, user_id="u", query_embedding=[0.0], top_k=5, **kw))
         add("memory_store.search_memories", kw, s.seen)
+
+    course = load(REF / "utu/rag/knowledge_retrieval/chroma_retrical_text2sql.py", "CourseSearcher", "search")
+
+    class CourseSelf:
+        def __init__(self):
+            self._embedding_cache, self.seen = {}, None
+            outer = self
+
+            class Emb:
+                async def embed_query(self, q):
+                    return [1.0, 0.0]
+
+            class VS:
+                async def search(self, query_embedding, top_k, filters):
+                    outer.seen = filters
+                    return []
+
+            self.embedder, self.vector_store = Emb(), VS()
+
+    for conds in (None, [{"type": "table_schema"}],
+                  [{"type": "column_value"}, {"table_name": "t1"}, {"column_name": "col2"}],      # the value-link loop's shape
+                  [{"type": "column_value"}, {"table_name": "t0"}, {"column_name": "col0"}],
+                  [{"type": "column_value"}, {"table_name": {"$in": ["t0", "t2"]}}]):
+        s = CourseSelf()
+        asyncio.run(course(s, query="q", top_k=3, filter_conditions=conds))
+        add("text2sql.CourseSearcher.search", {"filter_conditions": conds}, s.seen)
 
     metas = sample_metadata()
     for c in cases:

@@ -119,7 +119,9 @@ def test_filters_emitted_by_the_reference_toolkits_compile_and_evaluate():
             assert case["rows"] is None
             continue
         validate_where(where)
-        assert normalize_filters(where) == where          # toolkit output is already in operator form: passed verbatim
+        handed = normalize_filters(where)                 # what the store hands the engine (chroma_store.py:104-116)
+        assert handed == where or set(where) == set(handed) and all(handed[k] == {"$eq": v} for k, v in where.items())
+        assert np.array_equal(ow.eval_where(handed, metas), ow.eval_where(where, metas))
         want = np.zeros(len(metas), bool)
         want[case["rows"]] = True
         assert np.array_equal(ow.eval_where(where, metas), want), case["producer"]
