@@ -51,6 +51,14 @@ class _FakeCollection:
                 continue
             self.ids.append(i); self.emb.append(np.asarray(e, np.float32)); self.docs.append(d); self.metas.append(dict(m))
 
+    def upsert(self, ids, embeddings, documents, metadatas):
+        for i, e, d, m in zip(ids, embeddings, documents, metadatas):
+            if i in self.ids:
+                j = self.ids.index(i)
+                self.emb[j], self.docs[j], self.metas[j] = np.asarray(e, np.float32), d, dict(m)
+            else:
+                self.add([i], [e], [d], [m])
+
     def count(self):
         return len(self.ids)
 
@@ -104,6 +112,9 @@ class _FakeClient:
     def get_or_create_collection(self, name, metadata=None):
         return self.cols.setdefault(name, _FakeCollection(name, metadata))
 
+    def list_collections(self):
+        return list(self.cols.values())
+
     def delete_collection(self, name):
         self.cols.pop(name, None)
 
@@ -133,6 +144,8 @@ class _FakeFlat:
 def _install_fakes():
     chroma = types.ModuleType("chromadb")
     chroma.PersistentClient = _FakeClient
+    chroma.Client = _FakeClient
+    chroma.Collection = _FakeCollection
     cfg = types.ModuleType("chromadb.config")
     cfg.Settings = lambda **kw: kw
     chroma.config = cfg

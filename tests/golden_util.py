@@ -32,3 +32,83 @@ def compare_with_golden(results, want, tol, tie_eps=5e-7):
         if "metadata" in w and c.id == w["id"]:
             assert c.document_id == w["document_id"] and c.chunk_index == w["chunk_index"]
             assert c.content == w["content"] and c.metadata == w["metadata"]
+
+
+# ----------------------------------------------------------------------------- memory-store scenario (a6)
+def _to_chunk(Chunk, s):
+    from datetime import datetime
+
+    meta = dict(s["metadata"])
+    meta["created_at"] = datetime.fromisoformat(meta["created_at"])          # exercised: datetime -> isoformat on add
+    return Chunk(id=s["id"], document_id=s["document_id"], content=s["content"], chunk_index=s["chunk_index"],
+                 metadata=meta, embedding=s["embedding"])
+
+
+def _hit_json(pairs):
+    return [{"id": c.id, "document_id": c.document_id, "chunk_index": c.chunk_index, "content": c.content,
+             "metadata": c.metadata, "score": float(s)} for c, s in pairs]
+
+
+def _chunk_json(c):
+    return None if c is None else {"id": c.id, "document_id": c.document_id, "chunk_index": c.chunk_index, "content": c.content,
+                                   "metadata": c.metadata, "embedding": [float(v) for v in c.embedding] if c.embedding is not None else None}
+
+
+async def replay_memory_scenario(store, Chunk, specs, steps):
+    """Runs the scripted steps of tests/golden/memory_store.json on any store with MemoryVectorStore's interface
+    (the reference's, in the generator; B200MemoryVectorStore, in the tests); returns the JSON-able outputs."""
+    out = []
+    for name, kw in steps:
+        kw = dict(kw)
+        if name == "add_chunks":
+            await store.add_chunks([_to_chunk(Chunk, specs[i]) for i in kw["chunks"]], collection_name=kw["collection_name"])
+            out.append(None)
+        elif name == "upsert":
+            s = json.loads(json.dumps(specs[kw["chunk"]]))
+            s["embedding"] = specs[kw["new_embedding_from"]]["embedding"]
+            s["metadata"]["importance_score"] = kw["importance_score"]
+            await store.add_chunks([_to_chunk(Chunk, s)], collection_name=kw["collection_name"])
+            out.append(None)
+        elif name in ("search", "search_memories"):
+            q = specs[kw.pop("q")]["embedding"]
+            out.append(_hit_json(await getattr(store, name)(query_embedding=q, **kw)))
+        elif name == "get_working_memory":
+            out.append([_chunk_json(c) for c in await store.get_working_memory(**kw)])
+        elif name == "get_by_id":
+            out.append(_chunk_json(await store.get_by_id(**kw)))
+        elif name == "get_collection_name":
+            out.append(store.get_collection_name(**kw))
+        elif name == "delete_collection":
+            out.append(store.delete_collection(**kw))
+        else:
+            out.append(await getattr(store, name)(**kw))
+    return out
+
+
+def check_memory_outputs(golden, got, tol, emb_atol):
+    """Step-by-step comparison with the reference's outputs.  Search hits: ids in order (exact ties may swap),
+    scores within tol, document_id / chunk_index / content / parsed metadata equal.  Returned embeddings: the
+    reference hands back the vector as given, this backend the stored (unit-norm) one — compared after normalising."""
+    assert len(got) == len(golden["outputs"])
+    for (name, kw), want, have in zip(golden["steps"], golden["outputs"], got):
+        where = f"{name} {kw}"
+        if name in ("search", "search_memories"):
+            class _C:  # adapter for compare_with_golden
+                def __init__(self, h):
+                    self.id, self.document_id, self.chunk_index, self.content, self.metadata = (
+                        h["id"], h["document_id"], h["chunk_index"], h["content"], h["metadata"])
+            assert len(have) == len(want), where
+            compare_with_golden([(_C(h), h["score"]) for h in have], want, tol=tol)
+        elif name in ("get_working_memory", "get_by_id"):
+            w_list, h_list = (want, have) if name == "get_working_memory" else ([want], [have])
+            assert len(w_list) == len(h_list), where
+            for w, h in zip(w_list, h_list):
+                if w is None or h is None:
+                    assert w is None and h is None, where
+                    continue
+                assert {k: h[k] for k in ("id", "document_id", "chunk_index", "content", "metadata")} == \
+                       {k: w[k] for k in ("id", "document_id", "chunk_index", "content", "metadata")}, where
+                e = np.asarray(w["embedding"], np.float64)
+                np.testing.assert_allclose(np.asarray(h["embedding"], np.float64), e / np.linalg.norm(e), atol=emb_atol, err_msg=where)
+        else:
+            assert have == want, where

@@ -99,3 +99,18 @@ def test_rescoring_formulas():
     out = rank_skills([(s1[0], 0.8), (s2[0], 0.9), (s3[0], 0.95)], top_k=5, min_success_rate=0.3, tool_filter=["search"], now=now)
     assert [r[0].id for r in out] == ["s1"]
     assert abs(out[0][2] - (0.4 * 0.8 + 0.3 * 0.7 + 0.2 * 0.75 + 0.1 * 0.5)) < 1e-12
+
+
+def test_memory_store_replays_the_reference_scenario_on_the_device():
+    """tests/golden/memory_store.json — the reference's own MemoryVectorStore driven through a fixed
+    script — replayed on B200MemoryVectorStore with the real index underneath (fp32 storage: scores within 1e-5)."""
+    import json
+    from pathlib import Path
+
+    from tests.golden_util import check_memory_outputs, replay_memory_scenario
+
+    g = json.loads((Path(__file__).parent / "golden" / "memory_store.json").read_text())
+    store = B200MemoryVectorStore(VectorStoreConfig(backend="b200", collection_name="agent_memory",
+                                                    index_params={"storage_dtype": "f32"}))
+    got = asyncio.run(replay_memory_scenario(store, Chunk, g["specs"], g["steps"]))
+    check_memory_outputs(g, got, tol=1e-5, emb_atol=1e-6)

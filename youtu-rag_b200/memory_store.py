@@ -56,13 +56,7 @@ class B200MemoryVectorStore(BaseVectorStore):
         try:
             store = self._collections.pop(name, None)
             if store is not None:
-                import asyncio
-
-                loop = asyncio.new_event_loop()
-                try:
-                    loop.run_until_complete(store.clear())
-                finally:
-                    loop.close()
+                store.clear_sync()
                 store.close()
             return True
         except Exception as e:  # noqa: BLE001

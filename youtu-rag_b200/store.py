@@ -284,6 +284,11 @@ class B200VectorStore(BaseVectorStore):
         return len(self._row_of)
 
     async def clear(self) -> None:
+        self.clear_sync()
+
+    def clear_sync(self) -> None:
+        """Body of clear(); callable from synchronous code that already runs inside an event loop
+        (MemoryVectorStore.delete_collection is a plain method, memory_store.py:626-643)."""
         if self._index is not None:
             self._index.clear()
         self._ids, self._documents, self._metadatas, self._row_of = [], [], [], {}
