@@ -54,6 +54,23 @@ class FakeIndex:
     def read_rows(self, row_ids) -> np.ndarray:
         return self._rows[np.asarray(row_ids, np.int64)].copy()
 
+    def read_raw(self, row_begin: int, n: int):
+        """Rows as the device would hold them: [n, ld] bf16 bit patterns (uint16) or fp32, zero padded, + squared norms."""
+        ld = self.info()["ld"]
+        vals = np.zeros((n, ld), np.float32)
+        vals[:, :self.dim] = self._rows[row_begin:row_begin + n]
+        sq = (vals.astype(np.float32) ** 2).sum(1, dtype=np.float32)
+        return (ox.bf16_bits(vals) if self.dtype == "bf16" else vals), sq
+
+    def append_raw(self, rows: np.ndarray, sqnorm: np.ndarray) -> None:
+        ld = self.info()["ld"]
+        rows = np.asarray(rows)
+        if rows.ndim != 2 or rows.shape[1] != ld or np.asarray(sqnorm).shape[0] != rows.shape[0]:
+            raise ValueError(f"expected raw rows [n, {ld}] and n squared norms")
+        vals = ox.bf16_bits_to_f32(rows.astype(np.uint16)) if self.dtype == "bf16" else rows.astype(np.float32)
+        self._rows = np.concatenate([self._rows, vals[:, :self.dim]])
+        self._live = np.concatenate([self._live, np.ones(rows.shape[0], bool)])
+
     def set_live(self, row_ids, live: bool) -> None:
         self._live[np.asarray(row_ids, np.int64)] = bool(live)
 

@@ -22,12 +22,17 @@ def _oracle_behind_the_index(monkeypatch):
 
 # the GPU tests of the store, collected here without the gpu mark: same bodies, fake index underneath
 from tests.test_gpu_store import (  # noqa: E402,F401
+    test_persistence_roundtrip_is_bit_identical,
     test_retriever_over_b200_store_matches_reference_retriever,
     test_store_bf16_within_north_star_tolerance,
     test_store_edge_cases,
     test_store_mutations_match_reference_glue,
     test_store_reproduces_reference_glue_f32,
 )
+
+
+from tests.test_gpu_batched import test_per_query_filters  # noqa: E402,F401  (search_batch with one filter per query)
+from tests.test_gpu_memory_store import test_memory_store_matches_reference_semantics, test_rescoring_formulas  # noqa: E402,F401
 
 
 def test_memory_store_replays_the_reference_scenario():
