@@ -17,11 +17,11 @@ constexpr int UMMA_K = 16;
 constexpr int CAP = 256;       // candidate slots per (CTA, query)
 constexpr int MAX_Q = 256;     // queries per launch (2 query blocks)
 constexpr int QTILE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KiB: one query block x one k-block
-constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 32 KiB: one row tile x one k-block
+constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 16 KiB: one row tile x one k-block
 constexpr int MAX_TOPS = 2;
 
 __host__ __device__ constexpr int stages(int qb) { return (220 * 1024) / (qb * QTILE_BYTES + RTILE_BYTES); }
-// accumulator buffers in the 512 TMEM columns: QB=1 → 2 x 256, QB=2 → 1 x 512 (epilogue not overlapped)
+// accumulator buffers in the 512 TMEM columns: 2 x (QB x 128) columns, the epilogue of tile i overlaps tile i+1
 __host__ __device__ constexpr int acc_buffers(int qb) { return 512 / (qb * BLOCK_R) >= 2 ? 2 : 1; }
 __host__ __device__ constexpr int stage_bytes(int qb) { return qb * QTILE_BYTES + RTILE_BYTES; }
 
