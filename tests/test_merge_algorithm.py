@@ -100,3 +100,29 @@ def test_merge_when_one_list_holds_everything():
     out, n_out = merge_sorted_lists(lists, k)
     flat = np.sort(lists[lists != 0])[::-1][:k]
     assert n_out == k and np.array_equal(out, flat)
+
+
+def test_dense_staging_numbers_every_candidate_once():
+    """K3's dense staging (csrc/select.cuh): an exclusive prefix over the (clamped) segment lengths numbers the
+    candidates; candidate i belongs to the LAST segment whose offset is <= i, found by an 8-step binary search over
+    the 257 offsets (empty segments share offsets with their successor)."""
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        n_seg = int(rng.integers(1, 257))
+        cnt = np.zeros(256, np.int64)
+        cnt[:n_seg] = rng.choice([0, 0, 1, 2, 37, 256], size=n_seg)
+        off = np.zeros(257, np.int64)
+        off[1:] = np.cumsum(cnt)
+        total = int(off[256])
+        seen = np.zeros((256, 257), bool)
+        for i in rng.permutation(total)[:400] if total > 400 else range(total):
+            lo, hi = 0, 255
+            for _step in range(8):
+                mid = (lo + hi + 1) >> 1
+                if off[mid] <= i:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            assert lo < n_seg and off[lo] <= i < off[lo + 1] and 0 <= i - off[lo] < cnt[lo]
+            assert not seen[lo, i - off[lo]]
+            seen[lo, i - off[lo]] = True
