@@ -43,3 +43,88 @@ def test_memory_store_replays_the_reference_scenario():
                                                     index_params={"storage_dtype": "f32"}))
     got = asyncio.run(replay_memory_scenario(store, Chunk, g["specs"], g["steps"]))
     check_memory_outputs(g, got, tol=2e-6, emb_atol=1e-6)
+
+
+def test_store_bookkeeping_against_a_dict_model():
+    """Random add / re-add / upsert / delete / delete_by_document_id / delete_by_metadata / clear sequences: after
+    every step the store agrees with a plain dict model on count, get_by_id and a filtered exact search."""
+    from oracle import exact_search as ox
+    from oracle import where_eval as ow
+    from youtu_rag_b200 import B200VectorStore
+
+    rng = np.random.default_rng(17)
+    d = 12
+    s = B200VectorStore(VectorStoreConfig(collection_name="model", index_params={"storage_dtype": "f32"}))
+    model: dict[str, dict] = {}          # id -> {"emb", "meta", "content", "seq"}  (seq = order of the row in the store)
+    seq = 0
+
+    def mk(i):
+        return Chunk(id=f"c{i}", document_id=f"d{i % 4}", content=f"t{i}-{int(rng.integers(0, 99))}", chunk_index=i % 3,
+                     metadata={"source": f"f{i % 3}.pdf", "v": int(rng.integers(0, 10)), "opt": None if i % 2 else "x"},
+                     embedding=rng.standard_normal(d).astype(np.float32).tolist())
+
+    def put(c, replace):
+        nonlocal seq
+        if c.id in model and not replace:
+            return                                   # add_chunks ignores ids that already exist (collection.add)
+        meta = {"document_id": c.document_id, "chunk_index": c.chunk_index, **{k: v for k, v in c.metadata.items() if v is not None}}
+        model[c.id] = {"emb": np.asarray(c.embedding, np.float32), "meta": meta, "content": c.content, "seq": seq}
+        seq += 1
+
+    def check():
+        assert asyncio.run(s.count()) == len(model)
+        probe = [f"c{int(i)}" for i in rng.integers(0, 40, 4)]
+        for cid in probe:
+            got = asyncio.run(s.get_by_id(cid))
+            if cid not in model:
+                assert got is None
+            else:
+                assert (got.content, got.metadata) == (model[cid]["content"], model[cid]["meta"])
+        flt = [None, {"source": "f1.pdf"}, {"v": {"$gte": 5}}, {"$and": [{"document_id": "d2"}, {"v": {"$lt": 8}}]}][int(rng.integers(0, 4))]
+        q = rng.standard_normal(d).astype(np.float32)
+        got = asyncio.run(s.search(q.tolist(), top_k=5, filters=flt))
+        ids = sorted(model, key=lambda k: model[k]["seq"])                       # row order = insertion order of live rows
+        if ids:
+            rows = ox.prepare(np.stack([model[k]["emb"] for k in ids]), "cosine", "f32")
+            mask = ow.eval_where(ow.normalize_filters(flt), [model[k]["meta"] for k in ids])
+            wi, ws = ox.exact_topk(rows, ox.prepare(q, "cosine", "f32")[0], 5, "cosine", mask)
+            assert [c.id for c, _ in got] == [ids[i] for i in wi.tolist()]
+            np.testing.assert_allclose([sc for _, sc in got], ws, atol=1e-6)
+        else:
+            assert got == []
+
+    for step in range(120):
+        op = rng.choice(["add", "add", "readd", "upsert", "delete", "doc", "meta", "clear"], p=[.3, .2, .1, .12, .12, .07, .07, .02])
+        if op in ("add", "readd"):
+            cs = [mk(int(i)) for i in set(rng.integers(0, 40, int(rng.integers(1, 6))).tolist())]
+            asyncio.run(s.add_chunks(cs))
+            for c in cs:
+                put(c, replace=False)
+        elif op == "upsert":
+            cs = [mk(int(i)) for i in set(rng.integers(0, 40, 3).tolist())]
+            asyncio.run(s.upsert_chunks(cs))
+            for c in cs:
+                put(c, replace=True)
+        elif op == "delete":
+            ids = [f"c{int(i)}" for i in rng.integers(0, 40, 3)]
+            asyncio.run(s.delete(ids))
+            for i in ids:
+                model.pop(i, None)
+        elif op == "doc":
+            doc = f"d{int(rng.integers(0, 5))}"
+            n = asyncio.run(s.delete_by_document_id(doc))
+            gone = [k for k, v in model.items() if v["meta"]["document_id"] == doc]
+            assert n == len(gone)
+            for k in gone:
+                del model[k]
+        elif op == "meta":
+            f = {"source": f"f{int(rng.integers(0, 3))}.pdf", "chunk_index": int(rng.integers(0, 3))}
+            n = asyncio.run(s.delete_by_metadata(f))
+            gone = [k for k, v in model.items() if v["meta"]["source"] == f["source"] and v["meta"]["chunk_index"] == f["chunk_index"]]
+            assert n == len(gone)
+            for k in gone:
+                del model[k]
+        else:
+            asyncio.run(s.clear())
+            model.clear()
+        check()
