@@ -45,16 +45,20 @@ def test_memory_store_replays_the_reference_scenario():
     check_memory_outputs(g, got, tol=2e-6, emb_atol=1e-6)
 
 
-def test_store_bookkeeping_against_a_dict_model():
-    """Random add / re-add / upsert / delete / delete_by_document_id / delete_by_metadata / clear sequences: after
-    every step the store agrees with a plain dict model on count, get_by_id and a filtered exact search."""
+@pytest.mark.parametrize("persist", [False, True])
+def test_store_bookkeeping_against_a_dict_model(persist, tmp_path):
+    """Random add / re-add / upsert / delete / delete_by_document_id / delete_by_metadata / clear sequences (with
+    persistence: also close + reopen from disk at random points): after every step the store agrees with a plain
+    dict model on count, get_by_id and a filtered exact search."""
     from oracle import exact_search as ox
     from oracle import where_eval as ow
     from youtu_rag_b200 import B200VectorStore
 
     rng = np.random.default_rng(17)
     d = 12
-    s = B200VectorStore(VectorStoreConfig(collection_name="model", index_params={"storage_dtype": "f32"}))
+    cfg = VectorStoreConfig(collection_name="model", persist_directory=str(tmp_path),
+                            index_params={"storage_dtype": "f32", "persist": persist})
+    s = B200VectorStore(cfg)
     model: dict[str, dict] = {}          # id -> {"emb", "meta", "content", "seq"}  (seq = order of the row in the store)
     seq = 0
 
@@ -127,4 +131,7 @@ def test_store_bookkeeping_against_a_dict_model():
         else:
             asyncio.run(s.clear())
             model.clear()
+        if persist and rng.random() < 0.15:
+            s.close()
+            s = B200VectorStore(cfg)                 # reload: segments + tombstones
         check()
