@@ -177,7 +177,9 @@ def _load_reference():
     pkg("utu.rag.knowledge_retrieval", REF / "utu/rag/knowledge_retrieval")
     pkg("utu.rag.rerankers", REF / "utu/rag/rerankers")
     fac = types.ModuleType("utu.rag.rerankers.factory")
-    fac.RerankerFactory = type("RerankerFactory", (), {"create": staticmethod(lambda **kw: None)})
+    from tests.golden_util import GoldenReranker   # only reached with enable_reranking=True (base_retriever.py:34-39)
+
+    fac.RerankerFactory = type("RerankerFactory", (), {"create": staticmethod(lambda **kw: GoldenReranker())})
     sys.modules["utu.rag.rerankers.factory"] = fac
     mods = {}
     for name in ("utu.rag.base", "utu.rag.config", "utu.rag.storage.implementations.chroma_store",
@@ -313,6 +315,18 @@ def run():
                 single = await r.retrieve("1", **kw)
                 batch = await r.batch_retrieve(["0", "1", "2"], top_k=3, **kw)
                 out["retriever"].append({
+                    "config_threshold": thr, "kwargs": kw,
+                    "single": [{"id": x.chunk.id, "score": x.score, "rank": x.rank} for x in single],
+                    "batch": [[{"id": x.chunk.id, "score": x.score, "rank": x.rank} for x in b] for b in batch]})
+        # with a reranker: search 2k, threshold on the 2k hits, rerank to k, slice (base_retriever.py:61-80)
+        out["retriever_rerank"] = []
+        for thr in (0.0, 0.2):
+            rc = ref["config"].RetrieverConfig(top_k=4, similarity_threshold=thr, enable_reranking=True)
+            r = ref["base_retriever"].VectorRetriever(store, Emb(), rc)
+            for kw in ({}, {"filters": {"source": {"$in": ["file0.pdf", "file1.pdf"]}}}):
+                single = await r.retrieve("2", **kw)
+                batch = await r.batch_retrieve(["0", "1"], top_k=3, **kw)
+                out["retriever_rerank"].append({
                     "config_threshold": thr, "kwargs": kw,
                     "single": [{"id": x.chunk.id, "score": x.score, "rank": x.rank} for x in single],
                     "batch": [[{"id": x.chunk.id, "score": x.score, "rank": x.rank} for x in b] for b in batch]})

@@ -8,6 +8,22 @@ from youtu_rag_b200.base import Chunk
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "reference_glue.json").read_text())
 
 
+class GoldenReranker:
+    """Deterministic stand-in for the reference's HTTP rerankers (utu/rag/rerankers): orders hits by a hash of
+    (query, chunk id), gives them scores 0.9, 0.8, … and re-numbers the ranks.  Used on BOTH sides — by
+    make_golden.py under the reference's VectorRetriever and by the tests under this repo's."""
+
+    async def rerank(self, query, results, top_k=None):
+        import hashlib
+
+        def key(r):
+            return hashlib.md5(f"{query}|{r.chunk.id}".encode()).hexdigest()
+
+        out = sorted(results, key=key)
+        out = out[:top_k] if top_k else out
+        return [type(r)(chunk=r.chunk, score=round(0.9 - 0.1 * i, 6), rank=i + 1) for i, r in enumerate(out)]
+
+
 def golden_chunks():
     x = np.asarray(GOLDEN["corpus"]["embeddings"], np.float32)
     metas = GOLDEN["corpus"]["metadatas"]

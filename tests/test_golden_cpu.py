@@ -71,6 +71,24 @@ def test_retriever_mirror_reproduces_reference_retriever():
             compare_with_golden([(x.chunk, x.score) for x in got], want, tol=2e-6)
 
 
+def test_retriever_with_a_reranker_reproduces_reference_retriever():
+    """a7 with a reranker: 2k hits are fetched, thresholded, reranked to k and sliced (base_retriever.py:61-80); the
+    same deterministic reranker ran under the reference's VectorRetriever when the golden was made."""
+    from tests.golden_util import GoldenReranker
+
+    store = OracleStore("cosine", "f32")
+    asyncio.run(store.add_chunks(golden_chunks()))
+    for rec in GOLDEN["retriever_rerank"]:
+        cfg = RetrieverConfig(top_k=4, similarity_threshold=rec["config_threshold"], enable_reranking=True)
+        r = VectorRetriever(store, _Emb(), cfg, reranker=GoldenReranker())
+        single = asyncio.run(r.retrieve("2", **rec["kwargs"]))
+        batch = asyncio.run(r.batch_retrieve(["0", "1"], top_k=3, **rec["kwargs"]))
+        for got, want in [(single, rec["single"])] + list(zip(batch, rec["batch"])):
+            assert [(x.chunk.id, x.rank, x.score) for x in got] == [(w["id"], w["rank"], w["score"]) for w in want]
+    with pytest.raises(ValueError):
+        VectorRetriever(store, _Emb(), RetrieverConfig(enable_reranking=True))     # no silent skip without a reranker
+
+
 def test_context_assembler_reproduces_reference():
     from youtu_rag_b200.base import Chunk, RetrievalResult
     from youtu_rag_b200.postprocess import ContextAssembler, dedup_by_file, merge_results

@@ -35,6 +35,24 @@ from tests.test_gpu_batched import test_per_query_filters  # noqa: E402,F401  (s
 from tests.test_gpu_memory_store import test_memory_store_matches_reference_semantics, test_rescoring_formulas  # noqa: E402,F401
 
 
+def test_retriever_with_a_reranker_over_the_product_store():
+    """Same golden as tests/test_golden_cpu.py::test_retriever_with_a_reranker_reproduces_reference_retriever, but over
+    B200VectorStore (search_batch path of batch_retrieve included)."""
+    from tests.golden_util import GOLDEN, GoldenReranker, golden_chunks
+    from tests.test_gpu_store import _Emb
+    from youtu_rag_b200 import B200VectorStore, RetrieverConfig, VectorRetriever
+
+    s = B200VectorStore(VectorStoreConfig(collection_name="rr", index_params={"storage_dtype": "f32"}))
+    asyncio.run(s.add_chunks(golden_chunks()))
+    for rec in GOLDEN["retriever_rerank"]:
+        cfg = RetrieverConfig(top_k=4, similarity_threshold=rec["config_threshold"], enable_reranking=True)
+        r = VectorRetriever(s, _Emb(), cfg, reranker=GoldenReranker())
+        single = asyncio.run(r.retrieve("2", **rec["kwargs"]))
+        batch = asyncio.run(r.batch_retrieve(["0", "1"], top_k=3, **rec["kwargs"]))
+        for got, want in [(single, rec["single"])] + list(zip(batch, rec["batch"])):
+            assert [(x.chunk.id, x.rank, x.score) for x in got] == [(w["id"], w["rank"], w["score"]) for w in want]
+
+
 def test_memory_store_replays_the_reference_scenario():
     """every step of tests/golden/memory_store.json (the reference's MemoryVectorStore driven by
     tests/golden/make_memory_store_golden.py) gives the same outputs on B200MemoryVectorStore."""
