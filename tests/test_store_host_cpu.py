@@ -153,3 +153,23 @@ def test_store_bookkeeping_against_a_dict_model(persist, tmp_path):
             s.close()
             s = B200VectorStore(cfg)                 # reload: segments + tombstones
         check()
+
+
+def test_delete_collection_and_orphan_cleanup(tmp_path):
+    from tests.golden_util import GOLDEN, golden_chunks
+    from youtu_rag_b200 import B200VectorStore
+
+    cfg = VectorStoreConfig(collection_name="kb1", persist_directory=str(tmp_path), index_params={"persist": True, "storage_dtype": "f32"})
+    s = B200VectorStore(cfg)
+    asyncio.run(s.add_chunks(golden_chunks()[:20]))
+    assert (tmp_path / "kb1.b200" / "manifest.json").exists()
+    (tmp_path / "torn.b200").mkdir()                       # a writer died before its first manifest
+    (tmp_path / "other_dir").mkdir()
+    assert B200VectorStore.cleanup_orphaned_directories(str(tmp_path)) == {"deleted_count": 1, "deleted_dirs": ["torn.b200"]}
+    assert (tmp_path / "kb1.b200").exists() and (tmp_path / "other_dir").exists()
+    assert hasattr(s, "delete_collection")                 # what KnowledgeCleanupManager probes (cleanup_manager.py:651)
+    s.delete_collection()
+    assert not (tmp_path / "kb1.b200").exists()
+    again = B200VectorStore(cfg)                            # a fresh, empty collection of the same name
+    assert asyncio.run(again.count()) == 0 and asyncio.run(again.search(GOLDEN["queries"][0], 3)) == []
+    assert B200VectorStore.cleanup_orphaned_directories(str(tmp_path / "missing")) == {"deleted_count": 0, "deleted_dirs": []}

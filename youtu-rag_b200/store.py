@@ -299,6 +299,29 @@ class B200VectorStore(BaseVectorStore):
         logger.info("Cleared B200 collection: %s", self.config.collection_name)
 
     # ------------------------------------------------------------------ extras
+    def delete_collection(self) -> None:
+        """Delete the collection permanently, its on-disk directory included (chroma_store.py:331-398; probed with
+        hasattr and called synchronously by KnowledgeCleanupManager, cleanup_manager.py:651-652)."""
+        self.clear_sync()
+        self.close()
+
+    @staticmethod
+    def cleanup_orphaned_directories(persist_directory: str) -> dict:
+        """Remove collection directories a crashed writer left without a manifest (the counterpart of
+        chroma_store.py:274-329, which removes segment directories Chroma's index no longer lists).
+        Returns {"deleted_count": int, "deleted_dirs": list} like the reference."""
+        import shutil
+        from pathlib import Path
+
+        root = Path(persist_directory)
+        deleted: list[str] = []
+        if root.exists():
+            for item in sorted(root.iterdir()):
+                if item.is_dir() and item.name.endswith(".b200") and not (item / "manifest.json").exists():
+                    shutil.rmtree(item)
+                    deleted.append(item.name)
+        return {"deleted_count": len(deleted), "deleted_dirs": deleted}
+
     def close(self) -> None:
         if self._index is not None:
             self._index.close()
