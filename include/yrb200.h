@@ -87,6 +87,9 @@ YRB_API int yrb_index_append_raw(yrb_index* ix, const void* rows, const float* s
 /* collection.delete (chroma_store.py:150-160): tombstone / revive rows; tombstoned rows are
  * invisible to search. */
 YRB_API int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int live);
+/* Drop the rows appended last so that `rows` remain (rollback of a collection.add whose on-disk segment could not
+ * be written, chroma_store.py:86: memory and disk must not diverge). */
+YRB_API int yrb_index_truncate(yrb_index* ix, int64_t rows);
 /* client.delete_collection + recreate (chroma_store.py:257-272). */
 YRB_API int yrb_index_clear(yrb_index* ix);
 

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128, 1) probe(const unsigned char* __restrict_
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
     const long long t0 = clock64();
-    if (warp == 0 && lane == 0 && mode != 0) {
+    if (warp == 0 && lane == 0 && mode != 0 && mode != 4) {
         // filler: fill_bytes per k-block into the ring, paced only by its own completion two stages back
         const unsigned char* base = src + ((size_t)blockIdx.x * 65536) % (src_bytes - (size_t)P_STAGE_BYTES);
         int s = 0;
@@ -84,12 +84,21 @@ __global__ void __launch_bounds__(128, 1) probe(const unsigned char* __restrict_
         for (int it = 0; it < iters; ++it) {
             if (it >= P_STAGES) mbar_wait(mma_bar(s), ph ^ 1);  // bound the MMA queue: wait for the k-block issued 4 ago
             const uint32_t a0 = smem0 + s * P_STAGE_BYTES;
-            const uint64_t bdesc = smem_desc(a0 + 2 * QTILE_BYTES);
+            if (mode >= 4) {
+                // 128 queries x 256 rows per instruction: A = 16 KiB query block, B = 32 KiB (two row tiles back to back)
+                constexpr uint32_t IDESC256 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const uint64_t bdesc = smem_desc(a0 + QTILE_BYTES);
 #pragma unroll
-            for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
+                for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
+                    umma_bf16(tmem_base, smem_desc(a0) + 2 * k4, bdesc + 2 * k4, IDESC256, 1u);
+            } else {
+                const uint64_t bdesc = smem_desc(a0 + 2 * QTILE_BYTES);
 #pragma unroll
-                for (int qb = 0; qb < 2; ++qb)
-                    umma_bf16(tmem_base + qb * BLOCK_R, smem_desc(a0 + qb * QTILE_BYTES) + 2 * k4, bdesc + 2 * k4, IDESC, 1u);
+                for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4) {
+#pragma unroll
+                    for (int qb = 0; qb < 2; ++qb)
+                        umma_bf16(tmem_base + qb * BLOCK_R, smem_desc(a0 + qb * QTILE_BYTES) + 2 * k4, bdesc + 2 * k4, IDESC, 1u);
+                }
             }
             umma_commit(mma_bar(s));
             if (++s == P_STAGES) {
@@ -141,12 +150,22 @@ int main() {
         {1, P_STAGE_BYTES, "MMAs + 48 KiB fills per k-block (K2, 256 queries)"},
         {3, RTILE_BYTES, "MMAs + 16 KiB fills per k-block (rows only)"},
         {2, P_STAGE_BYTES, "48 KiB fills only"},
+        {4, 0, "N=256: MMAs only (4 x 128x256x16 per k-block)"},
+        {5, P_STAGE_BYTES, "N=256: MMAs + 48 KiB fills per k-block"},
+        {5, 2 * RTILE_BYTES, "N=256: MMAs + 32 KiB fills per k-block"},
     };
     for (const auto& r : runs) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        float ms = 0.f;
         for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaEventRecord(e0));
             probe<<<sms, 128, smem>>>(src, src_bytes, iters, r.mode, r.fill, clk);
             CK(cudaGetLastError());
+            CK(cudaEventRecord(e1));
             CK(cudaDeviceSynchronize());
+            CK(cudaEventElapsedTime(&ms, e0, e1));
         }
         long long* h = (long long*)malloc(sizeof(long long) * sms);
         CK(cudaMemcpy(h, clk, sizeof(long long) * sms, cudaMemcpyDeviceToHost));
@@ -155,7 +174,7 @@ int main() {
             avg += (double)h[i] / sms;
             if ((double)h[i] > mx) mx = (double)h[i];
         }
-        printf("%-52s  clk per k-block: avg %.1f  max %.1f   (512 = tensor pipe saturated)\n", r.what, avg / iters, mx / iters);
+        printf("%-52s  clk per k-block: avg %.1f  max %.1f   (512 = tensor pipe saturated)  %.2f ms, SM clock ~%.0f MHz\n", r.what, avg / iters, mx / iters, ms, mx / ms * 1e-3);
         free(h);
     }
     return 0;

@@ -77,6 +77,12 @@ class FakeIndex:
     def clear(self) -> None:
         self._rows, self._live, self._cols = np.zeros((0, self.dim), np.float32), np.zeros(0, bool), {}
 
+    def truncate(self, rows: int) -> None:
+        if not 0 <= rows <= self.rows:
+            raise native.NativeError(-1, f"truncate to {rows} rows: index holds {self.rows}")
+        self._rows, self._live = self._rows[:rows], self._live[:rows]
+        self._cols = {c: (t, v[:rows], p[:rows]) for c, (t, v, p) in self._cols.items()}
+
     # ------------------------------------------------------------ filter
     def column_write(self, col: int, col_type: int, row_begin: int, values: np.ndarray, present: np.ndarray) -> None:
         dt = {native.COL_I64: np.int64, native.COL_F64: np.float64, native.COL_CODE: np.int32, native.COL_BOOL: np.uint8}[col_type]

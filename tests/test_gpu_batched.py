@@ -109,7 +109,7 @@ def test_auto_path_uses_k2_for_batches_and_store_batch_api():
     from tests.golden_util import GOLDEN, golden_chunks
     from youtu_rag_b200 import B200VectorStore, VectorStoreConfig
 
-    s = B200VectorStore(VectorStoreConfig(collection_name="b"))
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_b"))
     asyncio.run(s.add_chunks(golden_chunks()))
     qs = np.asarray(GOLDEN["queries"] * 4, np.float32)          # 16 queries → batched kernel
     batch = asyncio.run(s.search_batch(qs, top_k=5, filters={"source": {"$in": ["file0.pdf", "file3.pdf"]}}))
@@ -143,7 +143,7 @@ def test_per_query_filters(nq):
     n, d = 6000, 64
     x = unit_rows(n, d, 41)
     metas = [{"table_name": f"t{i % 7}", "column_name": f"c{i % 3}", "type": "column_value", "v": i % 11} for i in range(n)]
-    s = B200VectorStore(VectorStoreConfig(collection_name="pq"))
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_pq"))
     asyncio.run(s.add_chunks([Chunk(id=f"r{i}", document_id="d", content="", chunk_index=i, metadata=metas[i],
                                     embedding=x[i].tolist()) for i in range(n)]))
     q = unit_rows(1, d, 42)[0]

@@ -32,10 +32,10 @@ def _memories(n, d, seed):
     return x, out, now
 
 
-def test_memory_store_matches_reference_semantics():
+def test_memory_store_matches_reference_semantics(tmp_path):
     n, d = 300, 32
     x, mem, now = _memories(n, d, 5)
-    s = B200MemoryVectorStore(VectorStoreConfig(collection_name="agent_memory"))
+    s = B200MemoryVectorStore(VectorStoreConfig(collection_name="agent_memory", persist_directory=str(tmp_path)))
     coll = s.get_collection_name("u1")
     assert coll == "memory_u1" and s.get_collection_name("u1", "procedural") == "memory_u1_procedural"
     run(s.add_chunks(mem, collection_name=coll))
@@ -101,7 +101,7 @@ def test_rescoring_formulas():
     assert abs(out[0][2] - (0.4 * 0.8 + 0.3 * 0.7 + 0.2 * 0.75 + 0.1 * 0.5)) < 1e-12
 
 
-def test_memory_store_replays_the_reference_scenario_on_the_device():
+def test_memory_store_replays_the_reference_scenario_on_the_device(tmp_path):
     """tests/golden/memory_store.json — the reference's own MemoryVectorStore driven through a fixed
     script — replayed on B200MemoryVectorStore with the real index underneath (fp32 storage: scores within 1e-5)."""
     import json
@@ -110,7 +110,7 @@ def test_memory_store_replays_the_reference_scenario_on_the_device():
     from tests.golden_util import check_memory_outputs, replay_memory_scenario
 
     g = json.loads((Path(__file__).parent / "golden" / "memory_store.json").read_text())
-    store = B200MemoryVectorStore(VectorStoreConfig(backend="b200", collection_name="agent_memory",
+    store = B200MemoryVectorStore(VectorStoreConfig(backend="b200", collection_name="agent_memory", persist_directory=str(tmp_path),
                                                     index_params={"storage_dtype": "f32"}))
     got = asyncio.run(replay_memory_scenario(store, Chunk, g["specs"], g["steps"]))
     check_memory_outputs(g, got, tol=1e-5, emb_atol=1e-6)

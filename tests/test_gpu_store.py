@@ -19,7 +19,7 @@ def run(c):
 
 
 def make(metric, dtype):
-    cfg = VectorStoreConfig(backend="b200", collection_name="t", distance_metric=metric,
+    cfg = VectorStoreConfig(backend="b200", collection_name="col_t", distance_metric=metric,
                             index_params={"storage_dtype": dtype})
     s = VectorStoreFactory.create(cfg)
     assert isinstance(s, B200VectorStore) and s.config.backend == "b200"
@@ -81,7 +81,7 @@ def test_store_mutations_match_reference_glue():
 
 
 def test_store_edge_cases():
-    s = B200VectorStore(VectorStoreConfig(collection_name="e"))
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_e"))
     assert run(s.search([0.0] * 8, 3)) == [] and run(s.count()) == 0
     run(s.add_chunks([]))
     ch = golden_chunks()
@@ -121,7 +121,7 @@ def test_retriever_over_b200_store_matches_reference_retriever():
 
 def test_persistence_roundtrip_is_bit_identical(tmp_path):
     """f1: add → delete → reopen from disk → same ids, same scores (bitwise), same metadata; then keep writing."""
-    cfg = VectorStoreConfig(collection_name="p", persist_directory=str(tmp_path), distance_metric="cosine",
+    cfg = VectorStoreConfig(collection_name="col_p", persist_directory=str(tmp_path), distance_metric="cosine",
                             index_params={"persist": True})
     a = B200VectorStore(cfg)
     ch = golden_chunks()
@@ -143,7 +143,7 @@ def test_persistence_roundtrip_is_bit_identical(tmp_path):
     c = B200VectorStore(cfg)
     assert run(c.count()) == n + 1 and run(c.get_by_id("doc0_chunk_0")) is not None
     run(c.clear())
-    assert not (tmp_path / "p.b200").exists()
+    assert not (tmp_path / "col_p.b200").exists()
     assert run(B200VectorStore(cfg).count()) == 0
 
 
@@ -157,7 +157,7 @@ def test_c1_config_through_the_store(dtype):
 
     n, d = 10_000, 1024
     x = unit_rows(n, d, 0)
-    s = B200VectorStore(VectorStoreConfig(collection_name="c1", distance_metric="cosine", index_params={"storage_dtype": dtype}))
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_c1", distance_metric="cosine", index_params={"storage_dtype": dtype}))
     for a in range(0, n, 2500):
         run(s.add_chunks([Chunk(id=f"k{i}", document_id=f"doc{i // 100}", content=f"chunk {i}", chunk_index=i % 100,
                                 embedding=x[i].tolist()) for i in range(a, a + 2500)]))

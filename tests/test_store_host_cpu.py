@@ -12,7 +12,7 @@ import pytest
 
 from tests.fake_index import FakeIndex
 from tests.golden_util import replay_memory_scenario, check_memory_outputs
-from youtu_rag_b200 import B200MemoryVectorStore, Chunk, VectorStoreConfig, native
+from youtu_rag_b200 import B200MemoryVectorStore, B200VectorStore, Chunk, VectorStoreConfig, native
 
 
 @pytest.fixture(autouse=True)
@@ -42,7 +42,7 @@ def test_retriever_with_a_reranker_over_the_product_store():
     from tests.test_gpu_store import _Emb
     from youtu_rag_b200 import B200VectorStore, RetrieverConfig, VectorRetriever
 
-    s = B200VectorStore(VectorStoreConfig(collection_name="rr", index_params={"storage_dtype": "f32"}))
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_rr", index_params={"storage_dtype": "f32"}))
     asyncio.run(s.add_chunks(golden_chunks()))
     for rec in GOLDEN["retriever_rerank"]:
         cfg = RetrieverConfig(top_k=4, similarity_threshold=rec["config_threshold"], enable_reranking=True)
@@ -53,11 +53,12 @@ def test_retriever_with_a_reranker_over_the_product_store():
             assert [(x.chunk.id, x.rank, x.score) for x in got] == [(w["id"], w["rank"], w["score"]) for w in want]
 
 
-def test_memory_store_replays_the_reference_scenario():
+def test_memory_store_replays_the_reference_scenario(tmp_path):
     """every step of tests/golden/memory_store.json (the reference's MemoryVectorStore driven by
     tests/golden/make_memory_store_golden.py) gives the same outputs on B200MemoryVectorStore."""
     g = json.loads((Path(__file__).parent / "golden" / "memory_store.json").read_text())
-    store = B200MemoryVectorStore(VectorStoreConfig(backend="b200", collection_name="agent_memory",
+    # the memory store persists by default, like the reference's PersistentClient (memory_store.py:183-199)
+    store = B200MemoryVectorStore(VectorStoreConfig(backend="b200", collection_name="agent_memory", persist_directory=str(tmp_path),
                                                     index_params={"storage_dtype": "f32"}))
     got = asyncio.run(replay_memory_scenario(store, Chunk, g["specs"], g["steps"]))
     check_memory_outputs(g, got, tol=2e-6, emb_atol=1e-6)
@@ -173,3 +174,74 @@ def test_delete_collection_and_orphan_cleanup(tmp_path):
     again = B200VectorStore(cfg)                            # a fresh, empty collection of the same name
     assert asyncio.run(again.count()) == 0 and asyncio.run(again.search(GOLDEN["queries"][0], 3)) == []
     assert B200VectorStore.cleanup_orphaned_directories(str(tmp_path / "missing")) == {"deleted_count": 0, "deleted_dirs": []}
+
+
+def test_collection_names_follow_chromas_rule(tmp_path):
+    """memory collections are named memory_<user id>; a name with a separator or '..' must never reach
+    mkdir / rmtree.  Chroma (the store this replaces) rejects the same names at create_collection."""
+    from youtu_rag_b200.persist import CollectionDir
+
+    for bad in ("../evil", "a/b", "..", "ab", "x" * 513, "a..b", "-abc", "abc-", "memory_../../etc"):
+        with pytest.raises(ValueError):
+            B200VectorStore(VectorStoreConfig(collection_name=bad, persist_directory=str(tmp_path)))
+        with pytest.raises(ValueError):
+            CollectionDir(str(tmp_path), bad)
+    mem = B200MemoryVectorStore(VectorStoreConfig(collection_name="agent_memory", persist_directory=str(tmp_path)))
+    assert mem.delete_collection("memory_../../x") is False          # swallowed like any engine error, nothing touched
+    B200VectorStore(VectorStoreConfig(collection_name="memory_user-1.a", persist_directory=str(tmp_path)))
+
+
+def test_memory_collections_are_listed_and_deleted_on_disk_after_a_restart(tmp_path):
+    """list_collections / delete_collection work on the persistent state (memory_store.py:617-643),
+    not only on collections this process has opened; memories persist by default."""
+    cfg = VectorStoreConfig(collection_name="agent_memory", persist_directory=str(tmp_path), index_params={"storage_dtype": "f32"})
+    a = B200MemoryVectorStore(cfg)
+    rng = np.random.default_rng(0)
+    chunk = Chunk(id="m1", document_id="d", content="hello", chunk_index=0, metadata={}, embedding=rng.standard_normal(8).tolist())
+    asyncio.run(a.add_chunks([chunk], collection_name="memory_u1"))
+    asyncio.run(a.add_chunks([chunk], collection_name="memory_u2"))
+    del a
+    b = B200MemoryVectorStore(cfg)                                    # "restart": nothing opened yet
+    assert b.list_collections() == ["memory_u1", "memory_u2"]
+    assert b.delete_collection("memory_u1") is True
+    assert not (tmp_path / "memory_u1.b200").exists()
+    assert b.list_collections() == ["memory_u2"]
+    assert asyncio.run(b.count("memory_u1")) == 0                     # recreated empty, not resurrected
+    assert asyncio.run(b.count("memory_u2")) == 1                     # the other one was reloaded from disk
+
+
+def test_add_is_all_or_nothing_and_numpy_metadata_is_coerced(tmp_path, monkeypatch):
+    """numpy scalars in metadata are stored as plain Python values (json-serialisable); a segment that
+    cannot be written rolls the device append back, so memory and disk agree; upsert persists the new row before
+    the tombstone."""
+    cfg = VectorStoreConfig(collection_name="kb_txn", persist_directory=str(tmp_path), index_params={"persist": True, "storage_dtype": "f32"})
+    s = B200VectorStore(cfg)
+    rng = np.random.default_rng(1)
+
+    def mk(i, **meta):
+        return Chunk(id=f"c{i}", document_id="d", content=f"t{i}", chunk_index=i, metadata=meta, embedding=rng.standard_normal(8).tolist())
+
+    asyncio.run(s.add_chunks([mk(0, n=np.int64(7), f=np.float32(0.5), b=np.bool_(True))]))
+    got = asyncio.run(s.get_by_id("c0")).metadata
+    assert got["n"] == 7 and type(got["n"]) is int and type(got["f"]) is float and got["b"] is True
+    # a failing disk write leaves nothing behind
+    from youtu_rag_b200 import persist
+
+    def boom(*a, **k):
+        raise OSError("disk full")
+
+    with monkeypatch.context() as mp:
+        mp.setattr(persist.CollectionDir, "append_segment", boom)
+        with pytest.raises(OSError):
+            asyncio.run(s.add_chunks([mk(1), mk(2)]))
+    assert asyncio.run(s.count()) == 1 and s.index.rows == 1 and asyncio.run(s.get_by_id("c1")) is None
+    asyncio.run(s.add_chunks([mk(1)]))
+    asyncio.run(s.upsert_chunks([mk(0, n=8)]))                        # replaces c0
+    assert asyncio.run(s.count()) == 2 and asyncio.run(s.get_by_id("c0")).metadata["n"] == 8
+    # crash between the new segment and the tombstone list: the reload still sees ONE c0, the newer one
+    (tmp_path / "kb_txn.b200" / "deleted.json").unlink()
+    s.close()
+    r = B200VectorStore(cfg)
+    assert asyncio.run(r.count()) == 2 and asyncio.run(r.get_by_id("c0")).metadata["n"] == 8
+    hits = asyncio.run(r.search(rng.standard_normal(8).tolist(), top_k=10))
+    assert sorted(c.id for c, _ in hits) == ["c0", "c1"]

@@ -914,6 +914,33 @@ int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int liv
     return upload_words(ix->d_live, ix->h_live, wmin, wmax + 1, ix->stream);
 }
 
+int yrb_index_truncate(yrb_index* ix, int64_t rows) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (rows < 0 || rows > ix->rows) return fail(YRB_ERR_INVALID, "truncate to %lld rows: index holds %lld", (long long)rows, (long long)ix->rows);
+    if (rows == ix->rows) return YRB_OK;
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ix->stream));
+    // rows [rows, ix->rows) disappear: their live / presence bits are cleared so a later append starts clean
+    const int64_t w0 = rows >> 5, w1 = ((ix->rows - 1) >> 5) + 1;
+    auto wipe = [&](std::vector<uint32_t>& bits, bool count_dead) {
+        for (int64_t r = rows; r < ix->rows; ++r) {
+            const uint32_t bit = 1u << (r & 31);
+            if (count_dead && !(bits[r >> 5] & bit)) ix->n_dead--;
+            bits[r >> 5] &= ~bit;
+        }
+    };
+    wipe(ix->h_live, true);
+    if ((rc = upload_words(ix->d_live, ix->h_live, w0, w1, ix->stream))) return rc;
+    for (auto& kv : ix->cols) {
+        wipe(kv.second.present_host, false);
+        if ((rc = upload_words(kv.second.present, kv.second.present_host, w0, w1, ix->stream))) return rc;
+    }
+    ix->rows = rows;
+    return YRB_OK;
+}
+
 int yrb_index_clear(yrb_index* ix) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);

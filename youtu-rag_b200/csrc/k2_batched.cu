@@ -124,22 +124,25 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     }
                 }
             }
-        } else if (lane == 0) {
+        } else {
+            // converged warp, one elected lane issues (see elect_one)
             int s = 0;
             uint32_t ph = 0;
+            const uint32_t piece_rows = (QB * BLOCK_Q) / CL;  // this CTA's slice of the query block (= the tensor map's box)
             for (int t = first; t < tile_end; t += step) {
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), SB);
-                    const uint32_t dst = smem0 + s * SB;
-                    // this CTA's slice of the query block: QB*128/CL query rows (= the tensor map's box)
-                    const uint32_t piece_rows = (QB * BLOCK_Q) / CL;
-                    if (CL == 1)
-                        tma_load_2d(dst, &tmap_q, full_bar(s), kb * BLOCK_K, 0);
-                    else
-                        tma_load_2d_mcast(dst + crank * piece_rows * (BLOCK_K * 2), &tmap_q, full_bar(s), kb * BLOCK_K,
-                                          (int)(crank * piece_rows), cmask);
-                    tma_load_2d(dst + QB * QTILE_BYTES, &tmap_r, full_bar(s), kb * BLOCK_K, t * BLOCK_R);
+                    if (elect_one()) {
+                        mbar_expect_tx(full_bar(s), SB);
+                        const uint32_t dst = smem0 + s * SB;
+                        if (CL == 1)
+                            tma_load_2d(dst, &tmap_q, full_bar(s), kb * BLOCK_K, 0);
+                        else
+                            tma_load_2d_mcast(dst + crank * piece_rows * (BLOCK_K * 2), &tmap_q, full_bar(s), kb * BLOCK_K,
+                                              (int)(crank * piece_rows), cmask);
+                        tma_load_2d(dst + QB * QTILE_BYTES, &tmap_r, full_bar(s), kb * BLOCK_K, t * BLOCK_R);
+                    }
+                    __syncwarp();
                     if (++s == S) {
                         s = 0;
                         ph ^= 1;
@@ -148,18 +151,19 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            int buf = 0;
-            uint32_t bph = 0;
-            for (int t = first; t < tile_end; t += step) {
-                mbar_wait(tempty_bar(buf), bph ^ 1);
+        // the whole warp walks the ring (every operand below is warp-uniform); one elected lane issues
+        int s = 0;
+        uint32_t ph = 0;
+        int buf = 0;
+        uint32_t bph = 0;
+        for (int t = first; t < tile_end; t += step) {
+            mbar_wait(tempty_bar(buf), bph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const uint32_t a0 = smem0 + s * SB;
+                const uint32_t a0 = smem0 + s * SB;
+                if (elect_one()) {
                     const uint64_t bdesc = smem_desc(a0 + QB * QTILE_BYTES);
                     // the two query blocks accumulate into different TMEM tiles: alternate them so that
                     // consecutive MMAs never depend on each other's accumulator
@@ -174,16 +178,17 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     }
                     if (CL == 1) umma_commit(empty_bar(s));
                     else umma_commit_mcast(empty_bar(s), cmask);
-                    if (++s == S) {
-                        s = 0;
-                        ph ^= 1;
-                    }
+                    if (kb == kblocks - 1) umma_commit(tfull_bar(buf));
                 }
-                umma_commit(tfull_bar(buf));
-                if (++buf == NBUF) {
-                    buf = 0;
-                    bph ^= 1;
+                __syncwarp();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
                 }
+            }
+            if (++buf == NBUF) {
+                buf = 0;
+                bph ^= 1;
             }
         }
     } else if (warp >= 4) {

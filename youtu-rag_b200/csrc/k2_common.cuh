@@ -79,6 +79,19 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
         : "memory");
 }
+// One lane of a converged warp (the compiler keeps warp-uniform operands of the predicated instructions in
+// uniform registers; an `if (lane == 0)` around a whole loop makes it re-elect a lane and move five registers to
+// the uniform file with R2UR for EVERY tcgen05 / TMA instruction — measured in round 2: the MMA issuer's own
+// instruction stream, not a barrier, was what K2 waited for).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

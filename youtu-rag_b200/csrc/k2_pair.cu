@@ -103,28 +103,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     const int pair = (int)blockIdx.x >> 1;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            const uint32_t lead_full0 = full_bar(0) & PEER_MASK;
-            for (int it = 0; it < iters; ++it) {
-                const int t = pair + it * n_pairs;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
+        // converged warps, one elected lane issues (see elect_one in k2_common.cuh)
+        int s = 0;
+        uint32_t ph = 0;
+        const uint32_t lead_full0 = full_bar(0) & PEER_MASK;
+        for (int it = 0; it < iters; ++it) {
+            const int t = pair + it * n_pairs;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(empty_bar(s), ph ^ 1);
+                if (elect_one()) {
                     if (leader) mbar_expect_tx(full_bar(s), 2 * PAIR_STAGE_BYTES);  // both CTAs' halves
                     const uint32_t dst = smem0 + s * PAIR_STAGE_BYTES;
                     const uint32_t lbar = lead_full0 + (uint32_t)s * 8u;
                     tma_load_2d_pair(dst, &tmap_q, lbar, kb * BLOCK_K, (int)crank * BLOCK_Q);
                     tma_load_2d_pair(dst + QTILE_BYTES, &tmap_r, lbar, kb * BLOCK_K, t * PAIR_N + (int)crank * 128);
-                    if (++s == S) {
-                        s = 0;
-                        ph ^= 1;
-                    }
+                }
+                __syncwarp();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        if (leader && lane == 0) {
+        if (leader) {
             int s = 0;
             uint32_t ph = 0;
             int buf = 0;
@@ -136,19 +138,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
                     const uint32_t a0 = smem0 + s * PAIR_STAGE_BYTES;
-                    const uint64_t adesc = smem_desc(a0);
-                    const uint64_t bdesc = smem_desc(a0 + QTILE_BYTES);
-                    const uint32_t d = tmem_base + buf * ACC_COLS;
+                    if (elect_one()) {
+                        const uint64_t adesc = smem_desc(a0);
+                        const uint64_t bdesc = smem_desc(a0 + QTILE_BYTES);
+                        const uint32_t d = tmem_base + buf * ACC_COLS;
 #pragma unroll
-                    for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
-                        umma_bf16_pair(d, adesc + 2 * k4, bdesc + 2 * k4, IDESC_PAIR, (kb | k4) != 0);
-                    umma_commit_pair(empty_bar(s));
+                        for (int k4 = 0; k4 < BLOCK_K / UMMA_K; ++k4)
+                            umma_bf16_pair(d, adesc + 2 * k4, bdesc + 2 * k4, IDESC_PAIR, (kb | k4) != 0);
+                        umma_commit_pair(empty_bar(s));
+                        if (kb == kblocks - 1) umma_commit_pair(tfull_bar(buf));
+                    }
+                    __syncwarp();
                     if (++s == S) {
                         s = 0;
                         ph ^= 1;
                     }
                 }
-                umma_commit_pair(tfull_bar(buf));
                 buf ^= 1;
                 if (buf == 0) bph ^= 1;
             }

@@ -18,8 +18,11 @@ import logging
 from datetime import datetime
 from typing import Any
 
+from pathlib import Path
+
 from .base import BaseVectorStore, Chunk
 from .config import VectorStoreConfig
+from .persist import CollectionDir
 from .store import B200VectorStore
 
 logger = logging.getLogger(__name__)
@@ -32,6 +35,9 @@ class B200MemoryVectorStore(BaseVectorStore):
         self.config = config
         self._persist_directory = persist_directory or (config.persist_directory if config else "./data/memory")
         self._params = dict(config.index_params) if config else {}
+        # the reference's memory store is a chromadb.PersistentClient (memory_store.py:183-199): memories survive
+        # the process.  Persistence is therefore ON unless index_params says otherwise.
+        self._params.setdefault("persist", True)
         self._collections: dict[str, B200VectorStore] = {}
         self._default_collection_name = config.collection_name if config else "agent_memory"
 
@@ -49,15 +55,25 @@ class B200MemoryVectorStore(BaseVectorStore):
         return self._collections[name]
 
     def list_collections(self) -> list[str]:
-        return sorted(self._collections)
+        """client.list_collections() (memory_store.py:617-624): what is on disk, opened in this process or not."""
+        names = set(self._collections)
+        root = Path(self._persist_directory)
+        if self._params.get("persist") and root.is_dir():
+            names.update(p.name[:-len(".b200")] for p in root.iterdir()
+                         if p.is_dir() and p.name.endswith(".b200") and (p / "manifest.json").exists())
+        return sorted(names)
 
     def delete_collection(self, collection_name: str | None = None) -> bool:
+        """client.delete_collection(name) (memory_store.py:626-643): works on the persistent state, so a collection
+        written by an earlier process is removed from disk even though this process never opened it."""
         name = collection_name or self._default_collection_name
         try:
             store = self._collections.pop(name, None)
             if store is not None:
                 store.clear_sync()
                 store.close()
+            if self._params.get("persist"):
+                CollectionDir(self._persist_directory, name).remove()
             return True
         except Exception as e:  # noqa: BLE001
             logger.warning("Failed to delete collection %s: %s", name, e)

@@ -61,8 +61,11 @@ class MetadataTable:
         self.rows = 0
 
     @staticmethod
-    def validate(meta: dict[str, Any]) -> None:
-        """Chroma rejects metadata values that are not str / int / float / bool."""
+    def validate(meta: dict[str, Any]) -> dict[str, Any]:
+        """Chroma rejects metadata values that are not str / int / float / bool.  Returns the dict with numpy
+        scalars (np.int64, np.float32, np.bool_ …) coerced to plain Python values, so that what is kept on the
+        host, written to disk (json) and returned in Chunk.metadata is what Chroma would hand back."""
+        out: dict[str, Any] = {}
         for k, v in meta.items():
             if not isinstance(k, str):
                 raise ValueError(f"Expected metadata key to be a str, got {k!r}")
@@ -71,6 +74,9 @@ class MetadataTable:
                 raise ValueError(f"Expected metadata value to be a str, int, float or bool, got {v!r} for key {k!r}")
             if t == native.COL_I64 and not (_I64_MIN <= int(v) <= _I64_MAX):
                 raise ValueError(f"metadata int {v} for key {k!r} does not fit in int64")
+            out[k] = (bool(v) if t == native.COL_BOOL else int(v) if t == native.COL_I64
+                      else float(v) if t == native.COL_F64 else str(v))
+        return out
 
     def append(self, metadatas: list[dict[str, Any]]) -> None:
         """Rows [self.rows, self.rows+len) get these metadata dicts (already validated)."""

@@ -30,7 +30,7 @@ WHERE_MAX_LEAVES, WHERE_MAX_OPERANDS, WHERE_MAX_TOKENS = 64, 256, 160
 EXPORTS = (
     "yrb_abi_version", "yrb_last_error", "yrb_device_count", "yrb_index_create", "yrb_index_destroy",
     "yrb_index_reserve", "yrb_index_count", "yrb_index_info", "yrb_index_append_host_f32",
-    "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_read_raw", "yrb_index_append_raw", "yrb_index_set_live", "yrb_index_clear",
+    "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_read_raw", "yrb_index_append_raw", "yrb_index_set_live", "yrb_index_clear", "yrb_index_truncate",
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_exchange_handle_bytes", "yrb_exchange_last_error", "yrb_exchange_create",
@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
     L.yrb_index_append_raw.argtypes = [vp, vp, vp, i64]
     L.yrb_index_set_live.argtypes = [vp, vp, i64, i32]
     L.yrb_index_clear.argtypes = [vp]
+    L.yrb_index_truncate.argtypes = [vp, i64]
     L.yrb_index_column_write.argtypes = [vp, i32, i32, i64, i64, vp, vp]
     L.yrb_index_where.argtypes = [vp, C.POINTER(Where), vp, C.POINTER(i64)]
     L.yrb_index_search.argtypes = [vp, vp, i32, i32, C.POINTER(Where), vp, vp, vp, vp]
@@ -215,6 +216,9 @@ class Index:
 
     def clear(self) -> None:
         _ck(lib().yrb_index_clear(self._h))
+
+    def truncate(self, rows: int) -> None:
+        _ck(lib().yrb_index_truncate(self._h, rows))
 
     # ------------------------------------------------------------ filter
     def column_write(self, col: int, col_type: int, row_begin: int, values: np.ndarray, present: np.ndarray) -> None:

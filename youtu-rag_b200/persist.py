@@ -16,6 +16,7 @@ small tombstone list, clear() removes the directory.  Loading replays the segmen
 from __future__ import annotations
 
 import json
+import re
 import shutil
 from pathlib import Path
 
@@ -24,9 +25,28 @@ import numpy as np
 VERSION = 1
 
 
+_NAME_RE = re.compile(r"^[a-zA-Z0-9][a-zA-Z0-9._-]{1,510}[a-zA-Z0-9]$")
+
+
+def validate_collection_name(name: str) -> str:
+    """Chroma's collection-name rule (the store this one replaces rejects the same names): 3-512 characters
+    from [a-zA-Z0-9._-], starting and ending with an alphanumeric, no "..".  Memory collections are named
+    `memory_<user_id>` (memory_store.py:209-223) with a caller-supplied user id, so a separator or ".." here
+    would let mkdir / rmtree leave `persist_directory`."""
+    if not isinstance(name, str) or not _NAME_RE.match(name) or ".." in name:
+        raise ValueError(
+            f"Expected collection name that (1) contains 3-512 characters from [a-zA-Z0-9._-], (2) starts and "
+            f"ends with a character in [a-zA-Z0-9] and (3) contains no two consecutive periods, got {name!r}")
+    return name
+
+
 class CollectionDir:
     def __init__(self, persist_directory: str, collection_name: str):
-        self.path = Path(persist_directory) / f"{collection_name}.b200"
+        validate_collection_name(collection_name)
+        root = Path(persist_directory).resolve()
+        self.path = root / f"{collection_name}.b200"
+        if self.path.resolve().parent != root:   # belt and braces: a symlinked component cannot escape either
+            raise ValueError(f"collection {collection_name!r} resolves outside {persist_directory!r}")
 
     def exists(self) -> bool:
         return (self.path / "manifest.json").exists()
@@ -46,13 +66,22 @@ class CollectionDir:
     def append_segment(self, rows: np.ndarray, sqnorm: np.ndarray, ids, documents, metadatas) -> None:
         m = self.manifest()
         stem = self.path / f"seg_{m['segments']:06d}"
+        # serialise first: a value json cannot encode fails before anything touches the disk
+        lines = [json.dumps({"id": i, "document": d, "metadata": md}, ensure_ascii=False)
+                 for i, d, md in zip(ids, documents, metadatas)]
         np.save(f"{stem}.rows.npy", rows)
         np.save(f"{stem}.sqnorm.npy", sqnorm)
         with open(f"{stem}.meta.jsonl", "w", encoding="utf-8") as f:
-            for i, d, md in zip(ids, documents, metadatas):
-                f.write(json.dumps({"id": i, "document": d, "metadata": md}, ensure_ascii=False) + "\n")
+            f.write("\n".join(lines) + "\n")
         m["segments"] += 1
         self._write_manifest(m)  # the manifest is written last: a torn segment is simply not listed
+
+    def truncate_segments(self, n: int) -> None:
+        """Forget segments >= n (rollback of an add whose device append failed after the segment was written)."""
+        m = self.manifest()
+        if m["segments"] > n:
+            m["segments"] = n
+            self._write_manifest(m)
 
     def segments(self):
         for s in range(self.manifest()["segments"]):

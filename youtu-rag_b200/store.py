@@ -28,7 +28,7 @@ from . import native
 from .base import BaseVectorStore, Chunk
 from .config import VectorStoreConfig
 from .metadata import MetadataTable
-from .persist import CollectionDir
+from .persist import CollectionDir, validate_collection_name
 from .where import compile_where, normalize_filters
 
 logger = logging.getLogger(__name__)
@@ -41,6 +41,7 @@ class B200VectorStore(BaseVectorStore):
 
     def __init__(self, config: VectorStoreConfig):
         self.config = config
+        validate_collection_name(config.collection_name)   # Chroma's create_collection rejects the same names
         p = dict(getattr(config, "index_params", None) or {})
         self._dtype = p.get("storage_dtype", "bf16")
         if self._dtype not in native.DTYPES:
@@ -105,16 +106,19 @@ class B200VectorStore(BaseVectorStore):
         if (m["metric"], m["dtype"]) != (self._metric, self._dtype):
             raise ValueError(f"collection on disk is {m['metric']}/{m['dtype']}, config asks {self._metric}/{self._dtype}")
         index = self._ensure_index(m["dim"])
+        superseded: list[int] = []
         for rows, sqnorm, recs in self._dir.segments():
             base = index.rows
             index.append_raw(rows, sqnorm)
             for i, r in enumerate(recs):
+                if r["id"] in self._row_of:       # upserted: the later segment wins even if the tombstone list
+                    superseded.append(self._row_of[r["id"]])   # was not rewritten before a crash
                 self._row_of[r["id"]] = base + i
             self._ids.extend(r["id"] for r in recs)
             self._documents.extend(r["document"] for r in recs)
             self._metadatas.extend(r["metadata"] for r in recs)
             self._meta.append([r["metadata"] for r in recs])
-        gone = [r for r in self._dir.deleted() if 0 <= r < index.rows]
+        gone = sorted({r for r in self._dir.deleted() if 0 <= r < index.rows} | set(superseded))
         if gone:
             index.set_live(gone, False)
             for r in gone:
@@ -133,50 +137,71 @@ class B200VectorStore(BaseVectorStore):
             if c.id in seen:
                 raise ValueError(f"Expected IDs to be unique, found duplicates of: {c.id}")
             seen.add(c.id)
-            if c.embedding is None:
-                raise ValueError(f"Chunk {c.id} has no embedding")
         fresh = [c for c in chunks if c.id not in self._row_of]
         if len(fresh) != len(chunks):
             # Chroma's add() leaves existing ids untouched
             logger.warning("Add of %d existing chunk ids ignored", len(chunks) - len(fresh))
+        self._append(fresh)
+
+    def _append(self, fresh: list[Chunk]) -> list[int]:
+        """Append chunks as new rows (ids may already exist: the caller tombstones the rows they replace).
+        Everything that can be rejected is checked before the first mutation; the on-disk segment is written
+        before the host tables change, and a failed write rolls the device append back, so memory and disk
+        never diverge.  Returns the rows the ids pointed at before (upsert)."""
         if not fresh:
-            return
+            return []
+        for c in fresh:
+            if c.embedding is None:
+                raise ValueError(f"Chunk {c.id} has no embedding")
         emb = np.asarray([c.embedding for c in fresh], dtype=np.float32)
         if emb.ndim != 2:
             raise ValueError("Expected every embedding to have the same dimension")
         if not np.isfinite(emb).all():
             raise ValueError("Embeddings contain NaN or infinite values")
-        metas = []
-        for c in fresh:
-            m = {"document_id": c.document_id, "chunk_index": c.chunk_index,
-                 **{k: v for k, v in (c.metadata or {}).items() if v is not None}}
-            MetadataTable.validate(m)
-            metas.append(m)
+        metas = [MetadataTable.validate({"document_id": c.document_id, "chunk_index": c.chunk_index,
+                                         **{k: v for k, v in (c.metadata or {}).items() if v is not None}})
+                 for c in fresh]
         index = self._ensure_index(emb.shape[1])
         base = index.rows
         assert base == len(self._ids) == self._meta.rows
         index.append(emb)
+        if self._dir is not None:
+            try:
+                if not self._dir.exists():
+                    self._dir.create(index.dim, self._metric, self._dtype, index.info()["ld"])
+                raw, sq = index.read_raw(base, len(fresh))   # exactly what the device holds
+                self._dir.append_segment(raw, sq, [c.id for c in fresh], [c.content for c in fresh], metas)
+            except BaseException:
+                index.truncate(base)   # the rows never became visible to a search
+                raise
+        replaced = [self._row_of[c.id] for c in fresh if c.id in self._row_of]
         for i, c in enumerate(fresh):
             self._row_of[c.id] = base + i
         self._ids.extend(c.id for c in fresh)
         self._documents.extend(c.content for c in fresh)
         self._metadatas.extend(metas)
         self._meta.append(metas)
-        if self._dir is not None:
-            if not self._dir.exists():
-                self._dir.create(index.dim, self._metric, self._dtype, index.info()["ld"])
-            raw, sq = index.read_raw(base, len(fresh))   # exactly what the device holds
-            self._dir.append_segment(raw, sq, [c.id for c in fresh], [c.content for c in fresh], metas)
         logger.info("Added %d chunks to B200 index", len(fresh))
+        return replaced
+
+    def _tombstone(self, rows: list[int]) -> None:
+        if not rows:
+            return
+        self._index.set_live(rows, False)
+        for r in rows:
+            self._ids[r] = self._documents[r] = self._metadatas[r] = None
+        if self._dir is not None:
+            self._deleted.update(rows)
+            self._dir.write_deleted(list(self._deleted))
 
     async def upsert_chunks(self, chunks: list[Chunk]) -> None:
-        """collection.upsert (memory_store.py:278-283): an existing id is replaced — its old row is
-        tombstoned and the new embedding / text / metadata appended."""
+        """collection.upsert (memory_store.py:278-283): an existing id is replaced — the new embedding / text /
+        metadata are appended (and persisted) first, then the old row is tombstoned, so a failure in between
+        leaves the record present; a reload treats an id seen again in a later segment the same way."""
         if not chunks:
             return
         last = {c.id: c for c in chunks}            # within one call the last occurrence of an id wins
-        await self.delete([cid for cid in last if cid in self._row_of])
-        await self.add_chunks(list(last.values()))
+        self._tombstone(self._append(list(last.values())))
 
     async def get_where(self, where: dict[str, Any] | None, include_embeddings: bool = False) -> list[Chunk]:
         """collection.get(where=…) (memory_store.py:442-451): every live chunk passing the filter, in row order."""
@@ -241,14 +266,8 @@ class B200VectorStore(BaseVectorStore):
     async def delete(self, chunk_ids: list[str]) -> None:
         if not chunk_ids:
             return
-        rows = [self._row_of.pop(cid) for cid in chunk_ids if cid in self._row_of]
-        if rows:
-            self._index.set_live(rows, False)
-            for r in rows:
-                self._ids[r] = self._documents[r] = self._metadatas[r] = None
-            if self._dir is not None:
-                self._deleted.update(rows)
-                self._dir.write_deleted(list(self._deleted))
+        rows = [self._row_of.pop(cid) for cid in dict.fromkeys(chunk_ids) if cid in self._row_of]
+        self._tombstone(rows)
         logger.info("Deleted %d chunks from B200 index", len(rows))
 
     async def delete_by_document_id(self, document_id: str) -> int:
