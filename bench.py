@@ -52,6 +52,7 @@ WORKLOADS = {
     "c5": (100_000_000, 768, 1024, 10, None),
     "tiny": (250_000, 1024, 1, 10, None),
     "t10mb": (10_000_000, 1024, 256, 100, None),   # 256-query batches over the 10M corpus (near-linear scaling case)
+    "c5s": (12_500_000, 768, 1024, 10, None),        # one C5 shard (12.5M x 768 per GPU of the 8-GPU config)
     "c3s": (125_000, 1024, 256, 100, None),        # one C3 shard of an 8-GPU run, for the fixed-cost breakdown
 }
 N_QUERY_SETS = 64

@@ -13,13 +13,13 @@
 #include <string>
 #include <vector>
 
-#include "../../include/yrb200.h"
-#include "k2_batched.h"
-#include "kernels.h"
+#include "index_internal.h"
+
+namespace yrbi {
 
 namespace {
-
 thread_local std::string g_err;
+}
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -30,92 +30,16 @@ int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-
-#define CK(call)                                                                                     \
-    do {                                                                                             \
-        cudaError_t e_ = (call);                                                                     \
-        if (e_ != cudaSuccess)                                                                       \
-            return fail(e_ == cudaErrorMemoryAllocation ? YRB_ERR_NOMEM : YRB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                                 \
-    } while (0)
-
-struct Column {
-    int type = -1;
-    void* values = nullptr;       // device, capacity rows
-    uint32_t* present = nullptr;  // device bitmask, capacity words
-    std::vector<uint32_t> present_host;
-};
+const std::string& last_error() { return g_err; }
+void set_error(const std::string& m) { g_err = m; }
 
 int col_width(int t) { return t == YRB_COL_I64 || t == YRB_COL_F64 ? 8 : (t == YRB_COL_CODE ? 4 : 1); }
 
-int64_t mask_words(int64_t rows) { return (((rows + 31) / 32) + 1) & ~int64_t(1); }
+}  // namespace yrbi
 
-}  // namespace
+using namespace yrbi;
 
-struct yrb_index {
-    int device = 0, dim = 0, ld = 0, metric = 0, dtype = 0, sm_count = 148;
-    int64_t rows = 0, capacity = 0, n_dead = 0;
-    void* d_rows = nullptr;
-    float* d_sqnorm = nullptr;
-    uint32_t* d_live = nullptr;  // mask_words(capacity)
-    uint32_t* d_mask = nullptr;  // filter scratch, same size
-    uint32_t* d_usermask = nullptr;  // device copy of a caller-supplied host bitmask, same size
-    std::vector<uint32_t> h_live;
-    std::map<int, Column> cols;
-    cudaStream_t stream = nullptr;
-    // search scratch
-    int nq_cap = 0, k_cap = 0;
-    float* d_qf32 = nullptr;
-    void* d_q = nullptr;
-    float* d_qsq = nullptr;
-    uint64_t* d_parts = nullptr;
-    uint64_t* d_keys = nullptr;
-    unsigned char* d_result = nullptr;  // [ids nq*k i64 | scores nq*k f32 | counts nq i32], one D2H
-    unsigned char* d_result_host = nullptr;  // device alias of h_result (pinned, mapped): small results are written there
-    size_t result_bytes = 0;
-    int64_t* d_ids = nullptr;           // views into d_result for the current (nq, k)
-    float* d_scores = nullptr;
-    int32_t* d_counts = nullptr;
-    unsigned int* d_ticket = nullptr;   // K1's last-CTA-done counter
-    unsigned long long* d_k1trace = nullptr;  // YRB_K1_TRACE=1: per-CTA phase stamps of the last K1 launch
-    // K8 compaction scratch (grow-only)
-    uint32_t* d_cp_blocks = nullptr;
-    size_t cp_blocks_cap = 0;
-    void* d_cp_rows = nullptr;
-    float* d_cp_sqnorm = nullptr;
-    uint32_t* d_cp_map = nullptr;
-    int64_t cp_rows_cap = 0;
-    unsigned long long* h_pass = nullptr;  // pinned
-    uint64_t* d_rowkeys = nullptr;  // K6: one key per row, allocated on first use
-    int64_t rowkeys_cap = 0;
-    void* d_select = nullptr;
-    size_t select_bytes = 0;
-    yrb::WhereProgDev* d_prog = nullptr;
-    yrb::WhereProgDev* h_prog = nullptr;  // pinned
-    yrb::WhereProgDev* d_progs = nullptr;  // per-query filters of a batch
-    yrb::WhereProgDev* h_progs = nullptr;
-    size_t progs_cap = 0;
-    uint32_t* d_qmasks = nullptr;          // [nq][mask_words]
-    size_t qmasks_bytes = 0;
-    unsigned long long* d_pass = nullptr;
-    // pinned staging
-    float* h_q = nullptr;
-    unsigned char* h_result = nullptr;
-    void* h_stage = nullptr;
-    size_t stage_bytes = 0;
-    yrb::K2State* k2 = nullptr;
-    int path = 0;
-    int reserved_sms = 0;
-    int64_t launches = 0;
-    bool prof = false;
-    std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
-    size_t prof_used = 0;
-    double prof_ms = 0.0;
-    int64_t prof_n = 0;
-    std::mutex mu;
-};
-
-namespace {
+namespace yrbi {
 
 int set_dev(const yrb_index* ix) {
     CK(cudaSetDevice(ix->device));
@@ -429,7 +353,8 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
 // raw fp32 queries [nq, dim] on the device → nq*k keys (and, when `decode`, ix->d_ids/d_scores/d_counts).
 // K1 prepares the query in its own prologue; K2 needs the prepared bf16 matrix (K5 launch).
 int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, int64_t mask_q_stride,
-                uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st) {
+                uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st, const yrb::XShard* xs) {
+    if (xs) ids = nullptr, scores = nullptr, counts = nullptr;  // the cross-shard merge writes the results
     const bool decode = ids != nullptr;
     const int sms = std::max(2, ix->sm_count - ix->reserved_sms) & ~1;  // even: K2 runs CTA clusters of 2
     int path = ix->path;
@@ -507,13 +432,21 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         cudaEvent_t ea, eb;
         int rc = prof_pair(ix, &ea, &eb);
         if (rc) return rc;
+        std::string err;
+        // compacted keys carry compact row numbers until K8 maps them back: the cross-shard finish then runs on its own
         rc = yrb::k2_search(ix->k2, k2_rows, k2_n, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
                             mask_q_stride, ix->metric, ix->d_qsq, k2_sqnorm, out_keys, ids, scores, counts, sms, st,
-                            &launches, g_err, ea, eb, pair, (compacted && use_rowmap) ? ix->d_cp_map : nullptr, ix->rows);
+                            &launches, err, ea, eb, pair, (compacted && use_rowmap) ? ix->d_cp_map : nullptr, ix->rows,
+                            compacted ? nullptr : xs);
+        if (rc) set_error(err);
         ix->launches += launches;
         if (!rc && compacted) {
             CK(yrb::launch_compact_remap(ix->d_cp_map, (int64_t)nq * k, out_keys, ids, st));
             ix->launches++;
+            if (xs) {
+                CK(yrb::launch_xshard_finish(*xs, out_keys, nq, k, st));
+                ix->launches++;
+            }
         }
         return rc;
     }
@@ -530,7 +463,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         }
         // one selection launch for the whole batch: query q's per-CTA lists sit at d_parts[q][cta][k]
         CK(yrb::launch_select_segments(ix->d_parts, k, (int64_t)parts * k, nullptr, 0, 0, parts, k, k, nullptr, nq, k, out_keys, st,
-                                       ids, scores, counts));
+                                       ids, scores, counts, xs));
         ix->launches++;
         return YRB_OK;
     }
@@ -540,6 +473,13 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             uint64_t* pk = ix->d_parts + (size_t)j * parts * k;
             yrb::K1Out o{out_keys + (size_t)j * k, ids ? ids + (size_t)j * k : nullptr,
                          scores ? scores + (size_t)j * k : nullptr, counts ? counts + j : nullptr};
+            yrb::XShard xj{};
+            if (xs) {
+                xj = *xs;
+                xj.q0 += j;
+                o.use_xs = 1;
+                o.xs = xj;
+            }
             bool fused = false;
             static const bool trace = getenv("YRB_K1_TRACE") != nullptr;
             if (trace) {
@@ -585,7 +525,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             }
             if (!fused) {
                 CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, parts, k, k, nullptr, 1, k, o.final_keys, st, o.ids,
-                                               o.scores, o.count));
+                                               o.scores, o.count, xs ? &xj : nullptr));
                 ix->launches++;
             }
         }
@@ -616,6 +556,38 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         CK(yrb::launch_decode(out_keys, nq, k, ids, scores, counts, st));
         ix->launches++;
     }
+    if (xs) {
+        CK(yrb::launch_xshard_finish(*xs, out_keys, nq, k, st));
+        ix->launches++;
+    }
+    return YRB_OK;
+}
+
+int upload_user_mask(yrb_index* ix, const uint32_t* mask, const uint32_t** out, cudaStream_t st) {
+    uint32_t* d_user = ix->d_usermask;
+    const int64_t nw = (ix->rows + 31) / 32, nwp = mask_words(ix->rows);
+    cudaError_t e = cudaMemsetAsync(d_user, 0, (size_t)nwp * 4, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_user, mask, (size_t)nw * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && (ix->rows & 31)) {
+        // clear bits past the last row of the last word
+        uint32_t last = mask[nw - 1] & ((1u << (ix->rows & 31)) - 1u);
+        e = cudaMemcpyAsync(d_user + nw - 1, &last, 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (e != cudaSuccess) return fail(YRB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
+    *out = d_user;
+    return YRB_OK;
+}
+
+int ensure_column(yrb_index* ix, int col, int col_type) {
+    Column& c = ix->cols[col];
+    if (c.type >= 0) return c.type == col_type ? YRB_OK : fail(YRB_ERR_INVALID, "column %d already has type %d", col, c.type);
+    int rc;
+    const size_t w = col_width(col_type);
+    c.type = col_type;
+    if ((rc = regrow(reinterpret_cast<char**>(&c.values), 0, (size_t)ix->capacity * w, true, ix->stream))) return rc;
+    if ((rc = regrow(&c.present, 0, (size_t)mask_words(ix->capacity) * 4, true, ix->stream))) return rc;
+    c.present_host.assign(mask_words(ix->capacity), 0u);
     return YRB_OK;
 }
 
@@ -634,12 +606,12 @@ int append_device_locked(yrb_index* ix, const float* dev_rows, int64_t n, cudaSt
     return YRB_OK;
 }
 
-}  // namespace
+}  // namespace yrbi
 
 extern "C" {
 
 int yrb_abi_version(void) { return YRB_ABI_VERSION; }
-const char* yrb_last_error(void) { return g_err.c_str(); }
+const char* yrb_last_error(void) { return last_error().c_str(); }
 
 int yrb_device_count(int* out_count) {
     if (!out_count) return fail(YRB_ERR_INVALID, "out_count is NULL");
@@ -972,16 +944,9 @@ int yrb_index_column_write(yrb_index* ix, int col, int col_type, int64_t row_beg
     if (rc) return rc;
     if (row_begin + n > ix->rows) return fail(YRB_ERR_INVALID, "column rows [%lld,%lld) beyond appended rows %lld",
                                                (long long)row_begin, (long long)(row_begin + n), (long long)ix->rows);
+    if ((rc = ensure_column(ix, col, col_type))) return rc;
     Column& c = ix->cols[col];
     const size_t w = col_width(col_type);
-    if (c.type < 0) {
-        c.type = col_type;
-        if ((rc = regrow(reinterpret_cast<char**>(&c.values), 0, (size_t)ix->capacity * w, true, ix->stream))) return rc;
-        if ((rc = regrow(&c.present, 0, (size_t)mask_words(ix->capacity) * 4, true, ix->stream))) return rc;
-        c.present_host.assign(mask_words(ix->capacity), 0u);
-    } else if (c.type != col_type) {
-        return fail(YRB_ERR_INVALID, "column %d already has type %d", col, c.type);
-    }
     CK(cudaMemcpyAsync(reinterpret_cast<char*>(c.values) + (size_t)row_begin * w, values, (size_t)n * w,
                        cudaMemcpyHostToDevice, ix->stream));
     for (int64_t i = 0; i < n; ++i) {
@@ -1046,20 +1011,7 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     const bool zero_copy = zc_enabled && ix->d_result_host && (size_t)nq * ke * 12 + (size_t)nq * 4 <= ZERO_COPY_RESULT_MAX;
     const size_t res_bytes = result_views(ix, nq, ke, zero_copy ? ix->d_result_host : ix->d_result);
     const uint32_t* dev_extra = nullptr;
-    if (mask) {
-        uint32_t* d_user = ix->d_usermask;
-        const int64_t nw = (ix->rows + 31) / 32, nwp = mask_words(ix->rows);
-        cudaError_t e = cudaMemsetAsync(d_user, 0, (size_t)nwp * 4, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_user, mask, (size_t)nw * 4, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess && (ix->rows & 31)) {
-            // clear bits past the last row of the last word
-            uint32_t last = mask[nw - 1] & ((1u << (ix->rows & 31)) - 1u);
-            e = cudaMemcpyAsync(d_user + nw - 1, &last, 4, cudaMemcpyHostToDevice, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        }
-        if (e != cudaSuccess) return fail(YRB_ERR_CUDA, "mask upload failed: %s", cudaGetErrorString(e));
-        dev_extra = d_user;
-    }
+    if (mask && (rc = upload_user_mask(ix, mask, &dev_extra, st))) return rc;
     const uint32_t* m = nullptr;
     int64_t m_stride = 0;
     if (per_query) {

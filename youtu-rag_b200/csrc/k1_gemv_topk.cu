@@ -445,6 +445,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
         if (s_last && fuse_stage > 0) {
             SelectArgs a{part_keys, k, 0, nullptr, 0, 0, (int)gridDim.x, k, k, nullptr, k, out.final_keys,
                          out.ids, out.scores, out.count};
+            a.use_xs = out.use_xs;
+            a.xs = out.xs;
             const int parts = (int)gridDim.x;
             if (KPL == 1 && parts <= 256) {
                 // k <= 32: stage the sorted per-CTA lists (one parallel round of L2 reads), then prune + rank
@@ -453,9 +455,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 for (int i = threadIdx.x; i < parts * k; i += blockDim.x) sk[i] = __ldcg(part_keys + i);
                 uint64_t* M = sk + parts * k;
                 MergeScratch* ms = reinterpret_cast<MergeScratch*>(M + K1_RANK_K * K1_RANK_K);
-                const int n_out =
-                    merge_sorted_lists(sk, parts, k, k, M, ms, [&](int slot, uint64_t key) { select_emit(a, 0, slot, key); }, dbg);
-                if (threadIdx.x == 0 && a.out_counts) a.out_counts[0] = n_out;
+                if (a.use_xs) {
+                    // sharded collection: the merged list goes to shared memory and from there to the cross-shard merge
+                    uint64_t* fin = reinterpret_cast<uint64_t*>(ms + 1);
+                    const int n_out = merge_sorted_lists(sk, parts, k, k, M, ms, [&](int slot, uint64_t key) { fin[slot] = key; }, dbg);
+                    xshard_finish(a.xs, 0, fin, n_out, sk);
+                } else {
+                    const int n_out =
+                        merge_sorted_lists(sk, parts, k, k, M, ms, [&](int slot, uint64_t key) { select_emit(a, 0, slot, key); }, dbg);
+                    if (threadIdx.x == 0 && a.out_counts) a.out_counts[0] = n_out;
+                }
             } else {
                 SelectScratch& S = *reinterpret_cast<SelectScratch*>(smem_raw + (size_t)fuse_stage * 8);
                 select_topk_block(a, 0, sk, fuse_stage, S);
@@ -654,7 +663,7 @@ static size_t k1_smem_bytes(int dtype, int nch, int k, int fuse_stage) {
     size_t m = (size_t)K1_WARPS * next_pow2(k) * sizeof(uint64_t) * 2 + sizeof(MergeScratch);  // lists + survivors
     size_t f = fuse_stage > 0 ? select_smem_bytes(fuse_stage) : 0;
     if (fuse_stage > 0 && k <= K1_RANK_K)  // staged lists + k x k matrix + scratch of the ranking merge
-        f = std::max(f, (size_t)fuse_stage * 8 + (size_t)K1_RANK_K * K1_RANK_K * 8 + sizeof(MergeScratch));
+        f = std::max(f, (size_t)fuse_stage * 8 + (size_t)K1_RANK_K * K1_RANK_K * 8 + sizeof(MergeScratch) + (size_t)K1_RANK_K * 8);
     size_t r = q > m ? q : m;
     return r > f ? r : f;
 }

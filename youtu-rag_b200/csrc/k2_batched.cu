@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "../../include/yrb200.h"
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                  int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                  float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
-                 int64_t mask_q_stride, const uint32_t* __restrict__ rowmap) {
+                 int64_t mask_q_stride, const uint32_t* __restrict__ rowmap, float* __restrict__ thr_out,
+                 unsigned int* __restrict__ sync_ctr) {
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
     constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
@@ -201,8 +203,13 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
         int cnt = active ? cand_cnt[slot] : 0;
         float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
         if (!active) thr = INFINITY;
-        float t0 = -INFINITY, t1 = -INFINITY;
-        const bool sample_only = tops != nullptr;  // phase A: publish the best scores, append nothing
+        float tops_l[MAX_TOPS];
+#pragma unroll
+        for (int i = 0; i < MAX_TOPS; ++i) tops_l[i] = -INFINITY;
+        // tops && thr_out: sampling fused into this launch (first tile read twice, see epi_exchange_thresholds);
+        // tops only: stand-alone sampling pass (publishes, appends nothing) — kept for non-cooperative launches
+        const bool fuse = tops != nullptr && thr_out != nullptr;
+        const bool sample_only = tops != nullptr && !fuse;
         // euclidean: score = 1 - ||q||^2 - ||x||^2 + 2 q.x (chroma_store.py:132-135 on the l2 space)
         const bool l2 = q_sqnorm != nullptr;
         const float l2_bias = (l2 && active) ? 1.f - q_sqnorm[qi] : 0.f;
@@ -214,75 +221,28 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
             mbar_wait(tfull_bar(buf), bph);
             tc_fence_after();
             const int64_t row0 = (int64_t)t * BLOCK_R;
+            const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + qb * BLOCK_R;
+            for (int pass = (fuse && t == first) ? 0 : 1; pass < 2; ++pass) {
+                const bool sampling = sample_only || pass == 0;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_R / 32; ++c) {
-                // make room for up to 32 appends: compact any lane's buffer that is nearly full
-                unsigned need = __ballot_sync(YRB_FULL, cnt > CAP - 32);
-                while (need) {
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int n = __shfl_sync(YRB_FULL, cnt, L);
-                    const uint64_t base = shfl_u64((uint64_t)buf_keys, L);
-                    uint64_t* bp = reinterpret_cast<uint64_t*>(base);
-                    uint64_t v[8];
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (i * 32 + lane < n) ? bp[i * 32 + lane] : 0ull;
-                    warp_sort256_desc(v, lane);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i * 32 + lane < k) bp[i * 32 + lane] = v[i];
-                    uint64_t kth = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint64_t x = shfl_u64(v[i], (k - 1) & 31);
-                        if (((k - 1) >> 5) == i) kth = x;
+                for (int c = 0; c < BLOCK_R / 32; ++c) {
+                    if (!sampling) epi_make_room(cnt, thr, buf_keys, k, lane);
+                    uint32_t v[32];
+                    tmem_ld32(tacc + c * 32, v);
+                    const int64_t r0 = row0 + c * 32;
+                    uint32_t mw = 0u;
+                    if (r0 < n_rows) {
+                        mw = qmask ? qmask[r0 >> 5] : 0xffffffffu;
+                        if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
+                        if (l2) epi_l2(v, l2_bias, row_sqnorm + r0);
                     }
-                    __syncwarp();
-                    if (lane == L) {
-                        cnt = n < k ? n : k;
-                        if (n >= k) thr = key_score(kth);
-                    }
+                    if (sampling) epi_sample(v, mw, tops_l);
+                    else epi_append(v, mw, thr, r0, buf_keys, cnt);
                 }
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + qb * BLOCK_R + c * 32, v);
-                const int64_t r0 = row0 + c * 32;
-                uint32_t mw = 0u;
-                if (r0 < n_rows) {
-                    mw = qmask ? qmask[r0 >> 5] : 0xffffffffu;
-                    if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
-                    if (l2) {
-                        const float4* xn = reinterpret_cast<const float4*>(row_sqnorm + r0);  // r0 is 32-aligned
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 n4 = xn[j4];   // padded: sqnorm is allocated in multiples of 256 rows
-                            v[4 * j4 + 0] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 0]), l2_bias - n4.x));
-                            v[4 * j4 + 1] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 1]), l2_bias - n4.y));
-                            v[4 * j4 + 2] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 2]), l2_bias - n4.z));
-                            v[4 * j4 + 3] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 3]), l2_bias - n4.w));
-                        }
-                    }
-                }
-                if (sample_only) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (((mw >> j) & 1u) && s > t1) {
-                            if (s > t0) {
-                                t1 = t0;
-                                t0 = s;
-                            } else {
-                                t1 = s;
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (((mw >> j) & 1u) && s > thr) buf_keys[cnt++] = make_key(s, (uint32_t)(r0 + j));
-                    }
-                }
+                if (pass == 0)
+                    thr = epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, (int)gridDim.x, 1, k, nq, qi, active,
+                                                  (int)blockIdx.x * 4 * QB + ew, (int)gridDim.x * 4 * QB, 128 * QB,
+                                                  threadIdx.x == 128, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -294,9 +254,10 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
         }
         if (active) {
             if (!sample_only) cand_cnt[slot] = cnt;
-            if (tops) {
-                tops[((int64_t)blockIdx.x * MAX_TOPS + 0) * MAX_Q + qi] = t0;
-                if (m_tops > 1) tops[((int64_t)blockIdx.x * MAX_TOPS + 1) * MAX_Q + qi] = t1;
+            if (sample_only) {
+#pragma unroll
+                for (int i = 0; i < MAX_TOPS; ++i)
+                    if (i < m_tops) tops[((int64_t)blockIdx.x * MAX_TOPS + i) * MAX_Q + qi] = tops_l[i];
             }
         }
     }
@@ -321,32 +282,8 @@ __global__ void __launch_bounds__(256) k2_threshold_kernel(const float* __restri
     const int lane = threadIdx.x & 31;
     const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (q >= nq) return;
-    const int n = n_cta * m;          // <= 2 * 148 + 32
-    uint32_t v[10];
-#pragma unroll
-    for (int j = 0; j < 10; ++j) {
-        const int i = lane + 32 * j;
-        float f = -INFINITY;
-        if (i < n) {
-            const int cta = (i / m) * cta_stride + (cta_stride == 2 && q >= BLOCK_Q ? 1 : 0);
-            f = tops[((int64_t)cta * MAX_TOPS + (i % m)) * MAX_Q + q];
-        }
-        v[j] = score_bits(f);
-    }
-    uint32_t t = 0;
-    if (n >= k) {
-        for (int bit = 31; bit >= 0; --bit) {
-            const uint32_t cand = t | (1u << bit);
-            int c = 0;
-#pragma unroll
-            for (int j = 0; j < 10; ++j) c += (lane + 32 * j < n) && (v[j] >= cand);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(YRB_FULL, c, o);
-            if (c >= k) t = cand;
-        }
-    }
-    // one ulp below the k-th published score: rows tying with it still pass the strict `s > thr`
-    if (lane == 0) thr0[q] = (n >= k) ? nextafterf(bits_score(t), -INFINITY) : -INFINITY;
+    const float t = warp_threshold(tops, n_cta, m, k, q, cta_stride, lane);
+    if (lane == 0) thr0[q] = t;
 }
 
 }  // namespace k2
@@ -406,7 +343,8 @@ template <int QB>
 static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows,
                                int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
                                const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const float* q_sqnorm,
-                               const float* row_sqnorm, int64_t mask_q_stride, const uint32_t* rowmap, cudaStream_t st) {
+                               const float* row_sqnorm, int64_t mask_q_stride, const uint32_t* rowmap, float* thr_out,
+                               unsigned int* sync_ctr, cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -416,21 +354,25 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     cfg.blockDim = dim3(128 + 128 * QB);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;   // the fused sampling meets grid-wide: every CTA must be resident
+    at[1].val.cooperative = thr_out != nullptr ? 1 : 0;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
-                              q_sqnorm, row_sqnorm, mask_q_stride, rowmap);
+                              q_sqnorm, row_sqnorm, mask_q_stride, rowmap, thr_out, sync_ctr);
 }
 
-// CTA-pair kernel for 129..256-query chunks (YRB_K2_PAIR=0 keeps the one-CTA kernel)
+// CTA-pair kernel for 129..256-query chunks — the default since round 2 (C3: 0.383 ms against 0.449 ms for the
+// one-CTA kernel, whose 128x128 SS-mode MMAs are bound by shared-memory operand reads); YRB_K2_PAIR=0 keeps the
+// one-CTA kernel for A/B runs
 static bool k2_use_pair(bool forced) {
     static int v = -1;
-    if (v < 0) v = getenv("YRB_K2_PAIR") ? atoi(getenv("YRB_K2_PAIR")) : 0;
+    if (v < 0) v = getenv("YRB_K2_PAIR") ? atoi(getenv("YRB_K2_PAIR")) : 1;
     return forced || v != 0;
 }
 
@@ -450,7 +392,8 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               int k, const uint32_t* mask_all, int64_t mask_q_stride, int metric, const float* q_sqnorm,
               const float* row_sqnorm, uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
               int* launches, std::string& err,
-              cudaEvent_t ev_start, cudaEvent_t ev_stop, bool force_pair, const uint32_t* rowmap, int64_t matrix_rows) {
+              cudaEvent_t ev_start, cudaEvent_t ev_stop, bool force_pair, const uint32_t* rowmap, int64_t matrix_rows,
+              const XShard* xs_in) {
     (void)capacity; (void)dim;
     if (rowmap) force_pair = false;  // the row-subset producer lives in the one-CTA kernel
     const float* xn = metric == YRB_METRIC_L2 ? row_sqnorm : nullptr;
@@ -472,7 +415,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (s->thr0) cudaFree(s->thr0);
         s->cand_keys = nullptr; s->cand_cnt = nullptr; s->tops = nullptr; s->thr0 = nullptr;
         K2CK(cudaMalloc(&s->cand_keys, (size_t)want_slots * k2::MAX_Q * k2::CAP * 8));
-        K2CK(cudaMalloc(&s->cand_cnt, (size_t)want_slots * k2::MAX_Q * 4));
+        K2CK(cudaMalloc(&s->cand_cnt, ((size_t)want_slots * k2::MAX_Q + 1) * 4));  // + the grid-barrier counter
         K2CK(cudaMalloc(&s->tops, (size_t)want_slots * k2::MAX_TOPS * k2::MAX_Q * 4));
         K2CK(cudaMalloc(&s->thr0, (size_t)k2::MAX_Q * 4));
         s->slots = want_slots;
@@ -487,43 +430,70 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         if (!make_map(s, &mr, rows, (uint64_t)matrix_rows, ld, gbox, err)) return YRB_ERR_CUDA;
     } else if (!make_map(s, &mr, rows, (uint64_t)n_rows, ld, k2::BLOCK_R, err)) return YRB_ERR_CUDA;
 
+    // sampling inside the main launch (cooperative) unless YRB_K2_FUSE=0 (the round-1 sequence: sampling launch,
+    // threshold kernel, main launch — kept for A/B runs)
+    static int fuse_env = -1;
+    if (fuse_env < 0) fuse_env = getenv("YRB_K2_FUSE") ? atoi(getenv("YRB_K2_FUSE")) : 1;
+    unsigned int* sync_ctr = reinterpret_cast<unsigned int*>(s->cand_cnt + (size_t)s->slots * k2::MAX_Q);  // zeroed with the counts
     for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
+        const bool fuse = fuse_env != 0;
         const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
         const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
         const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
+        uint64_t* o_keys = out_keys + (size_t)c0 * k;
+        int64_t* o_ids = out_ids ? out_ids + (size_t)c0 * k : nullptr;
+        float* o_scores = out_scores ? out_scores + (size_t)c0 * k : nullptr;
+        int32_t* o_counts = out_counts ? out_counts + c0 : nullptr;
+        XShard xs_c{};
+        const XShard* xs = nullptr;
+        if (xs_in) {
+            xs_c = *xs_in;
+            xs_c.q0 += c0;
+            xs = &xs_c;
+        }
+        K2CK(cudaMemsetAsync(s->cand_cnt, 0, ((size_t)s->slots * k2::MAX_Q + 1) * 4, st));
         if (nqc > k2::BLOCK_Q && !rowmap && k2_use_pair(force_pair)) {
             // CTA pairs (cta_group::2): 256-row tiles, CTA r of a pair owns queries [128r, 128r+128)
             const int tiles2 = (int)((n_rows + 255) / 256);
             int n_pairs = sm_count / 2;
             if (tiles2 < n_pairs) n_pairs = tiles2;
             const int grid2 = 2 * n_pairs;
+            const int iters2 = (tiles2 + n_pairs - 1) / n_pairs;
             CUtensorMap mq2;
             if (!make_map(s, &mq2, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)((nqc + 127) / 128 * 128), ld,
                           k2::BLOCK_Q, err))
                 return YRB_ERR_CUDA;
-            K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)s->slots * k2::MAX_Q * 4, st));
-            const int m_tops2 = (2 * k + n_pairs - 1) / n_pairs <= 1 ? 1 : k2::MAX_TOPS;
-            const bool sampled2 = tiles2 > 2 * n_pairs && (int64_t)n_pairs * m_tops2 >= k;
+            // thresholds: k-th largest of the best scores every pair publishes for its first tile — a valid lower bound
+            // of the k-th best overall as soon as n_pairs * m_tops >= k scores are published
+            const int m_tops2 = std::min(k2::MAX_TOPS, std::max(1, (3 * k + n_pairs - 1) / n_pairs));
+            const bool sampled2 = (int64_t)n_pairs * m_tops2 >= k && (fuse || tiles2 > 2 * n_pairs);
             const float* thr2 = nullptr;
-            if (sampled2) {
+            if (sampled2 && !fuse) {
                 K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, 1, nqc, k, mask, mask_q_stride, nullptr, s->cand_keys,
-                                      s->cand_cnt, s->tops, m_tops2, qn, xn, st));
+                                      s->cand_cnt, s->tops, m_tops2, qn, xn, nullptr, nullptr, st));
                 k2::k2_threshold_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(s->tops, n_pairs, m_tops2, k, s->thr0, 2, nqc);
                 K2CK(cudaGetLastError());
                 *launches += 2;
                 thr2 = s->thr0;
             }
-            const int iters2 = (tiles2 + n_pairs - 1) / n_pairs;
+            const bool fz = sampled2 && fuse;
             if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
-            K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, iters2, nqc, k, mask, mask_q_stride, thr2, s->cand_keys,
-                                  s->cand_cnt, nullptr, 0, qn, xn, st));
+            {
+                cudaError_t e = launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, iters2, nqc, k, mask, mask_q_stride, thr2, s->cand_keys,
+                                                 s->cand_cnt, fz ? s->tops : nullptr, fz ? m_tops2 : 0, qn, xn, fz ? s->thr0 : nullptr,
+                                                 fz ? sync_ctr : nullptr, st);
+                if (e != cudaSuccess && fz) {  // cooperative launch refused: redo this chunk with the separate sampling pass
+                    cudaGetLastError();
+                    fuse_env = 0;
+                    c0 -= k2::MAX_Q;
+                    continue;
+                }
+                K2CK(e);
+            }
             if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
             K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, grid2, 0,
-                                        k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st,
-                                        out_ids ? out_ids + (size_t)c0 * k : nullptr,
-                                        out_scores ? out_scores + (size_t)c0 * k : nullptr,
-                                        out_counts ? out_counts + c0 : nullptr));
+                                        k2::CAP, nullptr, nqc, k, o_keys, st, o_ids, o_scores, o_counts, xs));
             *launches += 2;
             continue;
         }
@@ -531,45 +501,44 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         int grid = tiles < sm_count ? tiles : sm_count;
         const int cluster = k2_cluster(sm_count);
         grid = (grid + cluster - 1) / cluster * cluster;
+        const int iters = (tiles + grid - 1) / grid;
         CUtensorMap mq;
         if (!make_map(s, &mq, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)((nqc + 127) / 128 * 128), ld,
                       QB * k2::BLOCK_Q / cluster, err))
             return YRB_ERR_CUDA;
-        K2CK(cudaMemsetAsync(s->cand_cnt, 0, (size_t)s->slots * k2::MAX_Q * 4, st));
-        // phase A (sampling): the first tile of each CTA is scored only to publish each query's best
-        // scores; thr0 = k-th largest of them is a valid lower bound of the k-th best overall.
+        auto gemm = [&](int it, const float* thr, float* tops, int m, float* thr_out, unsigned int* ctr) -> cudaError_t {
+            return QB == 2 ? launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, it, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
+                                            tops, m, qn, xn, mask_q_stride, rowmap, thr_out, ctr, st)
+                           : launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, it, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
+                                            tops, m, qn, xn, mask_q_stride, rowmap, thr_out, ctr, st);
+        };
+        // sampling: each CTA's first tile publishes its best scores per query (CTAs past the last tile publish -inf)
         const int gridA = tiles < grid ? tiles : grid;   // CTAs that see a real tile
-        const int m_tops = (2 * k + gridA - 1) / gridA <= 1 ? 1 : k2::MAX_TOPS;
-        const bool sampled = tiles > 2 * grid && (int64_t)gridA * m_tops >= k;
+        const int m_tops = std::min(k2::MAX_TOPS, std::max(1, (3 * k + gridA - 1) / gridA));
+        const bool sampled = (int64_t)gridA * m_tops >= k && (fuse || tiles > 2 * grid);
         const float* thr = nullptr;
-        if (sampled) {
-            if (QB == 2)
-                K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, rowmap, st));
-            else
-                K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, 1, nqc, k, mask, nullptr, s->cand_keys,
-                                    s->cand_cnt, s->tops, m_tops, qn, xn, mask_q_stride, rowmap, st));
+        if (sampled && !fuse) {
+            K2CK(gemm(1, nullptr, s->tops, m_tops, nullptr, nullptr));
             k2::k2_threshold_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(s->tops, gridA, m_tops, k, s->thr0, 1, nqc);
             K2CK(cudaGetLastError());
             *launches += 2;
             thr = s->thr0;
         }
-        // phase B: every tile, with the bound
-        const int iters = (tiles + grid - 1) / grid;
+        const bool fz = sampled && fuse;
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_start, st));
-        if (QB == 2)
-            K2CK(launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, rowmap, st));
-        else
-            K2CK(launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, iters, nqc, k, mask, thr, s->cand_keys,
-                                s->cand_cnt, nullptr, 0, qn, xn, mask_q_stride, rowmap, st));
+        {
+            cudaError_t e = gemm(iters, thr, fz ? s->tops : nullptr, fz ? m_tops : 0, fz ? s->thr0 : nullptr, fz ? sync_ctr : nullptr);
+            if (e != cudaSuccess && fz) {  // cooperative launch refused: redo this chunk with the separate sampling pass
+                cudaGetLastError();
+                fuse_env = 0;
+                c0 -= k2::MAX_Q;
+                continue;
+            }
+            K2CK(e);
+        }
         if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
-        const int gridB = grid;
-        K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, gridB, 0,
-                                    k2::CAP, nullptr, nqc, k, out_keys + (size_t)c0 * k, st,
-                                    out_ids ? out_ids + (size_t)c0 * k : nullptr,
-                                    out_scores ? out_scores + (size_t)c0 * k : nullptr,
-                                    out_counts ? out_counts + c0 : nullptr));
+        K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, grid, 0,
+                                    k2::CAP, nullptr, nqc, k, o_keys, st, o_ids, o_scores, o_counts, xs));
         *launches += 2;
     }
     return YRB_OK;

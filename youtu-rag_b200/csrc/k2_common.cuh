@@ -18,7 +18,7 @@ constexpr int CAP = 256;       // candidate slots per (CTA, query)
 constexpr int MAX_Q = 256;     // queries per launch (2 query blocks)
 constexpr int QTILE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KiB: one query block x one k-block
 constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 16 KiB: one row tile x one k-block
-constexpr int MAX_TOPS = 2;
+constexpr int MAX_TOPS = 4;   // best scores each (CTA, query) publishes in the sampling pass
 
 __host__ __device__ constexpr int stages(int qb) { return (220 * 1024) / (qb * QTILE_BYTES + RTILE_BYTES); }
 // accumulator buffers in the 512 TMEM columns: 2 x (QB x 128) columns, the epilogue of tile i overlaps tile i+1
@@ -183,6 +183,175 @@ __device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
     }
 }
 
+// ---------------------------------------------------------------- epilogue pieces shared by both kernels
+// An epilogue thread owns ONE query (TMEM lane); a chunk is 32 consecutive corpus rows (TMEM columns).
+// With one epilogue warp per scheduler every branch latency is exposed, and a compare-and-branch per score
+// made the epilogue, not the tensor pipe, the pace of the CTA-pair kernel (round-2 ncu: the MMA issuer waited on
+// tmem-empty 43 % of the time).  So the common path is branch-free: 32 compares build a survivor bitmask in four
+// independent chains, and only set bits — a handful per warp and chunk — take the append path, which fetches the
+// score with a select tree instead of dynamic register indexing.
+
+// survivors of one chunk: bit j set <=> score j beats the threshold
+__device__ __forceinline__ uint32_t epi_hits(const uint32_t (&v)[32], float thr) {
+    uint32_t h[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j & 3] |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+    return (h[0] | h[1]) | (h[2] | h[3]);
+}
+// v[j] for a run-time j without spilling v to local memory: five levels of selects
+__device__ __forceinline__ uint32_t epi_pick(const uint32_t (&v)[32], int j) {
+    uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+    return (j & 16) ? d[1] : d[0];
+}
+// append the chunk's survivors (rows r0 + j) to this thread's candidate buffer; the caller made room for 32
+__device__ __forceinline__ void epi_append(const uint32_t (&v)[32], uint32_t mw, float thr, int64_t r0,
+                                           uint64_t* __restrict__ buf_keys, int& cnt) {
+    uint32_t hit = epi_hits(v, thr) & mw;
+    while (hit) {
+        const int j = __ffs((int)hit) - 1;
+        hit &= hit - 1;
+        buf_keys[cnt++] = make_key(__uint_as_float(epi_pick(v, j)), (uint32_t)(r0 + j));
+    }
+}
+// phase A: the MAX_TOPS best scores seen so far (descending), a compare-exchange chain per score
+__device__ __forceinline__ void epi_sample(const uint32_t (&v)[32], uint32_t mw, float (&t)[MAX_TOPS]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float s = ((mw >> j) & 1u) ? __uint_as_float(v[j]) : -INFINITY;
+#pragma unroll
+        for (int i = 0; i < MAX_TOPS; ++i) {
+            const float lo = fminf(s, t[i]);
+            t[i] = fmaxf(s, t[i]);
+            s = lo;
+        }
+    }
+}
+// euclidean: score = 1 - ||q||^2 - ||x||^2 + 2 q.x (chroma_store.py:132-135 on the l2 space); xn = ||x||^2 of the
+// chunk's 32 rows (32-aligned; the array is padded to a multiple of 256 rows)
+__device__ __forceinline__ void epi_l2(uint32_t (&v)[32], float l2_bias, const float* __restrict__ xn) {
+    const float4* x4 = reinterpret_cast<const float4*>(xn);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 n4 = x4[j4];
+        v[4 * j4 + 0] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 0]), l2_bias - n4.x));
+        v[4 * j4 + 1] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 1]), l2_bias - n4.y));
+        v[4 * j4 + 2] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 2]), l2_bias - n4.z));
+        v[4 * j4 + 3] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 3]), l2_bias - n4.w));
+    }
+}
+// ---- in-kernel sampling (round 2: replaces the separate sampling launch + threshold kernel)
+// The first tile of every CTA stays in its TMEM buffer while the epilogue threads (a) read it once to publish
+// each query's best scores, (b) meet grid-wide, (c) turn the published scores into per-query thresholds — one
+// warp per query, spread over all CTAs —, (d) meet again, and then read the same accumulator a second time with the
+// bound.  The MMA warp keeps going on the other buffer meanwhile.  Needs every CTA resident: cooperative launch.
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all n_epi epilogue threads of every CTA; `ctr` counts CTAs, `target` = arrivals that complete this rendezvous
+__device__ __forceinline__ void epi_grid_barrier(unsigned int* ctr, unsigned int target, int n_epi, bool first_thread) {
+    __threadfence();
+    named_bar_sync(1, n_epi);
+    if (first_thread) {
+        atomicAdd(ctr, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u32(ctr) < target)
+            if (clock64() - t0 > 4000000000ll) __trap();  // a CTA never arrived: fail instead of hanging the GPU
+    }
+    named_bar_sync(1, n_epi);
+}
+// k-th largest of the n_cta * m published scores of query q, minus one ulp (rows tying with it still pass the strict
+// `s > thr`): every published score belongs to a distinct real row, so at least k rows reach it and it cannot exceed
+// the true k-th best.  Fewer than k published → -inf.  cta_stride 1: every CTA published for q; 2 (pair kernel):
+// CTA 2i + (q >= 128).  Bisection on the monotone bit patterns (32 rounds of compare + warp popcount); whole warp.
+__device__ __forceinline__ float warp_threshold(const float* tops, int n_cta, int m, int k, int q, int cta_stride, int lane) {
+    constexpr int NV = (148 + 16) * MAX_TOPS / 32 + 1;  // n <= (SMs + cluster padding) * MAX_TOPS
+    const int n = n_cta * m;
+    uint32_t v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = lane + 32 * j;
+        float f = -INFINITY;
+        if (i < n) {
+            const int cta = (i / m) * cta_stride + (cta_stride == 2 && q >= BLOCK_Q ? 1 : 0);
+            f = __ldcg(tops + ((int64_t)cta * MAX_TOPS + (i % m)) * MAX_Q + q);
+        }
+        v[j] = score_bits(f);
+    }
+    uint32_t t = 0;
+    if (n >= k) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = t | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) c += (lane + 32 * j < n) && (v[j] >= cand);
+            c = __reduce_add_sync(YRB_FULL, c);
+            if (c >= k) t = cand;
+        }
+    }
+    return (n >= k) ? nextafterf(bits_score(t), -INFINITY) : -INFINITY;
+}
+// steps (b)-(d) above.  epi_warp / n_epi_warps number the epilogue warps of the whole grid.
+__device__ __forceinline__ float epi_exchange_thresholds(const float (&tops_l)[MAX_TOPS], float* tops, int m_tops, float* thr_out,
+                                                         unsigned int* sync_ctr, int n_cta_pub, int cta_stride, int k, int nq,
+                                                         int qi, bool active, int epi_warp, int n_epi_warps, int n_epi_threads,
+                                                         bool first_thread, int lane) {
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < MAX_TOPS; ++i)
+            if (i < m_tops) tops[((int64_t)blockIdx.x * MAX_TOPS + i) * MAX_Q + qi] = tops_l[i];
+    }
+    epi_grid_barrier(sync_ctr, gridDim.x, n_epi_threads, first_thread);
+    for (int q = epi_warp; q < nq; q += n_epi_warps) {
+        const float t = warp_threshold(tops, n_cta_pub, m_tops, k, q, cta_stride, lane);
+        if (lane == 0) thr_out[q] = t;
+    }
+    epi_grid_barrier(sync_ctr, 2u * gridDim.x, n_epi_threads, first_thread);
+    return active ? __ldcg(thr_out + qi) : INFINITY;
+}
+
+// make room for up to 32 appends per lane: a lane whose buffer is nearly full has it compacted in place by the
+// whole warp (bitonic sort of the 256 slots, the best k stay) and its threshold raised to the k-th kept score
+__device__ __forceinline__ void epi_make_room(int& cnt, float& thr, uint64_t* buf_keys, int k, int lane) {
+    unsigned need = __ballot_sync(YRB_FULL, cnt > CAP - 32);
+    while (need) {
+        const int L = __ffs(need) - 1;
+        need &= need - 1;
+        const int n = __shfl_sync(YRB_FULL, cnt, L);
+        uint64_t* bp = reinterpret_cast<uint64_t*>(shfl_u64((uint64_t)buf_keys, L));
+        uint64_t v[8];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (i * 32 + lane < n) ? bp[i * 32 + lane] : 0ull;
+        warp_sort256_desc(v, lane);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i * 32 + lane < k) bp[i * 32 + lane] = v[i];
+        uint64_t kth = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint64_t x = shfl_u64(v[i], (k - 1) & 31);
+            if (((k - 1) >> 5) == i) kth = x;
+        }
+        __syncwarp();
+        if (lane == L) {
+            cnt = n < k ? n : k;
+            if (n >= k) thr = key_score(kth);
+        }
+    }
+}
 
 }  // namespace k2
 }  // namespace yrb

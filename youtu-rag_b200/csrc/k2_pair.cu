@@ -62,7 +62,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                       int kblocks, int iters, int nq, int k, const uint32_t* __restrict__ mask, int64_t mask_q_stride,
                       const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                       float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm,
-                      const float* __restrict__ row_sqnorm) {
+                      const float* __restrict__ row_sqnorm, float* __restrict__ thr_out, unsigned int* __restrict__ sync_ctr) {
     constexpr int S = PAIR_STAGES;
     constexpr int ACC_COLS = PAIR_N;  // per buffer; two buffers = all 512 columns
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -167,8 +167,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         int cnt = active ? cand_cnt[slot] : 0;
         float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
         if (!active) thr = INFINITY;
-        float t0 = -INFINITY, t1 = -INFINITY;
-        const bool sample_only = tops != nullptr;
+        float tops_l[MAX_TOPS];
+#pragma unroll
+        for (int i = 0; i < MAX_TOPS; ++i) tops_l[i] = -INFINITY;
+        // tops && thr_out: sampling fused into this launch (the first tile is read twice, epi_exchange_thresholds)
+        const bool fuse = tops != nullptr && thr_out != nullptr;
+        const bool sample_only = tops != nullptr && !fuse;
         const bool l2 = q_sqnorm != nullptr;
         const float l2_bias = (l2 && active) ? 1.f - q_sqnorm[qi] : 0.f;
         const uint32_t* qmask = mask ? mask + (active ? (int64_t)qi * mask_q_stride : 0) : nullptr;
@@ -179,74 +183,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
             mbar_wait(tfull_bar(buf), bph);
             tc_fence_after();
             const int64_t row0 = (int64_t)t * PAIR_N;
+            const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS;
+            for (int pass = (fuse && it == 0) ? 0 : 1; pass < 2; ++pass) {
+                const bool sampling = sample_only || pass == 0;
 #pragma unroll 1
-            for (int c = 0; c < PAIR_N / 32; ++c) {
-                unsigned need = __ballot_sync(YRB_FULL, cnt > CAP - 32);
-                while (need) {
-                    const int L = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int n = __shfl_sync(YRB_FULL, cnt, L);
-                    const uint64_t base = shfl_u64((uint64_t)buf_keys, L);
-                    uint64_t* bp = reinterpret_cast<uint64_t*>(base);
-                    uint64_t v[8];
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = (i * 32 + lane < n) ? bp[i * 32 + lane] : 0ull;
-                    warp_sort256_desc(v, lane);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i * 32 + lane < k) bp[i * 32 + lane] = v[i];
-                    uint64_t kth = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint64_t x = shfl_u64(v[i], (k - 1) & 31);
-                        if (((k - 1) >> 5) == i) kth = x;
+                for (int c = 0; c < PAIR_N / 32; ++c) {
+                    if (!sampling) epi_make_room(cnt, thr, buf_keys, k, lane);
+                    uint32_t v[32];
+                    tmem_ld32(tacc + c * 32, v);
+                    const int64_t r0 = row0 + c * 32;
+                    uint32_t mw = 0u;
+                    if (r0 < n_rows) {
+                        mw = qmask ? qmask[r0 >> 5] : 0xffffffffu;
+                        if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
+                        if (l2) epi_l2(v, l2_bias, row_sqnorm + r0);
                     }
-                    __syncwarp();
-                    if (lane == L) {
-                        cnt = n < k ? n : k;
-                        if (n >= k) thr = key_score(kth);
-                    }
+                    if (sampling) epi_sample(v, mw, tops_l);
+                    else epi_append(v, mw, thr, r0, buf_keys, cnt);
                 }
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * ACC_COLS + c * 32, v);
-                const int64_t r0 = row0 + c * 32;
-                uint32_t mw = 0u;
-                if (r0 < n_rows) {
-                    mw = qmask ? qmask[r0 >> 5] : 0xffffffffu;
-                    if (r0 + 32 > n_rows) mw &= (1u << (int)(n_rows - r0)) - 1u;
-                    if (l2) {
-                        const float4* xn = reinterpret_cast<const float4*>(row_sqnorm + r0);
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 n4 = xn[j4];
-                            v[4 * j4 + 0] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 0]), l2_bias - n4.x));
-                            v[4 * j4 + 1] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 1]), l2_bias - n4.y));
-                            v[4 * j4 + 2] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 2]), l2_bias - n4.z));
-                            v[4 * j4 + 3] = __float_as_uint(fmaf(2.f, __uint_as_float(v[4 * j4 + 3]), l2_bias - n4.w));
-                        }
-                    }
-                }
-                if (sample_only) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (((mw >> j) & 1u) && s > t1) {
-                            if (s > t0) {
-                                t1 = t0;
-                                t0 = s;
-                            } else {
-                                t1 = s;
-                            }
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = __uint_as_float(v[j]);
-                        if (((mw >> j) & 1u) && s > thr) buf_keys[cnt++] = make_key(s, (uint32_t)(r0 + j));
-                    }
-                }
+                if (pass == 0)   // CTA 2i + r published for the queries [128r, 128r + 128): n_pairs publishers per query
+                    thr = epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, n_pairs, 2, k, nq, qi, active,
+                                                  (int)blockIdx.x * 4 + quarter, (int)gridDim.x * 4, 128, threadIdx.x == 128, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -259,9 +216,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         }
         if (active) {
             if (!sample_only) cand_cnt[slot] = cnt;
-            if (tops) {
-                tops[((int64_t)blockIdx.x * MAX_TOPS + 0) * MAX_Q + qi] = t0;
-                if (m_tops > 1) tops[((int64_t)blockIdx.x * MAX_TOPS + 1) * MAX_Q + qi] = t1;
+            if (sample_only) {
+#pragma unroll
+                for (int i = 0; i < MAX_TOPS; ++i)
+                    if (i < m_tops) tops[((int64_t)blockIdx.x * MAX_TOPS + i) * MAX_Q + qi] = tops_l[i];
             }
         }
     }
@@ -280,13 +238,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks, int iters,
                              int nq, int k, const uint32_t* mask, int64_t mask_q_stride, const float* thr, uint64_t* ck,
                              int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm,
-                             cudaStream_t st) {
+                             float* thr_out, unsigned int* sync_ctr, cudaStream_t st) {
     const size_t smem = (size_t)k2::PAIR_STAGES * k2::PAIR_STAGE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(k2::k2_gemm_topk_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k2::k2_gemm_topk_pair<<<grid, 256, smem, st>>>(mq, mr, n_rows, kblocks, iters, nq, k, mask, mask_q_stride, thr, ck, cc,
-                                                   tops, m_tops, q_sqnorm, row_sqnorm);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // the fused sampling meets grid-wide: every CTA must be resident
+    at[0].val.cooperative = thr_out != nullptr ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k2::k2_gemm_topk_pair, mq, mr, n_rows, kblocks, iters, nq, k, mask, mask_q_stride, thr, ck, cc,
+                              tops, m_tops, q_sqnorm, row_sqnorm, thr_out, sync_ctr);
 }
 
 }  // namespace yrb

@@ -26,14 +26,44 @@ __global__ void __launch_bounds__(SEL_THREADS) select_segments_kernel(SelectArgs
 cudaError_t launch_select_segments(const uint64_t* base, int64_t seg_stride, int64_t q_stride, const int* counts,
                                    int64_t cnt_seg_stride, int64_t cnt_q_stride, int n_seg, int fixed_cnt, int seg_cap,
                                    const float* thr, int nq, int k, uint64_t* out, cudaStream_t st, int64_t* ids,
-                                   float* scores, int32_t* counts_out) {
+                                   float* scores, int32_t* counts_out, const XShard* xs) {
     if (k < 1 || k > SEL_KMAX || n_seg > SEL_MAX_SEG) return cudaErrorInvalidValue;
     const size_t smem = select_smem_bytes(SEL_STAGE);
     cudaError_t e = cudaFuncSetAttribute(select_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     SelectArgs a{base, seg_stride, q_stride, counts, cnt_seg_stride, cnt_q_stride, n_seg, fixed_cnt, seg_cap, thr, k, out,
                  ids, scores, counts_out};
+    if (xs) {
+        a.use_xs = 1;
+        a.xs = *xs;
+    }
     select_segments_kernel<<<nq, SEL_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// the cross-shard finish on its own (xshard.cuh): one CTA per query
+__global__ void __launch_bounds__(256) xshard_finish_kernel(XShard x, const uint64_t* __restrict__ local_keys, int k_local) {
+    extern __shared__ __align__(16) unsigned char sraw[];
+    uint64_t* stage = reinterpret_cast<uint64_t*>(sraw);
+    const uint64_t* mine = local_keys + (size_t)blockIdx.x * k_local;
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    int n = 0;
+    for (int i = threadIdx.x; i < k_local; i += blockDim.x) n += mine[i] != 0ull;
+    if (n) atomicAdd(&s_n, n);
+    __syncthreads();
+    xshard_finish(x, blockIdx.x, mine, s_n, stage);
+}
+
+cudaError_t launch_xshard_finish(const XShard& xs, const uint64_t* local_keys, int nq, int k_local, cudaStream_t st) {
+    const size_t smem = (size_t)xs.n_shards * xs.k * 8;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(xshard_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    xshard_finish_kernel<<<nq, 256, smem, st>>>(xs, local_keys, k_local);
     return cudaGetLastError();
 }
 

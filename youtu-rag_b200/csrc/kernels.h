@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "xshard.cuh"
+
 namespace yrb {
 
 struct DeviceInfo {
@@ -36,6 +38,8 @@ struct K1Out {
     float* scores;         // optional [k]
     int32_t* count;        // optional [1]
     unsigned long long* trace = nullptr;  // optional [grid][8] phase stamps (globaltimer ns), YRB_K1_TRACE
+    int use_xs = 0;                       // sharded collection: the last CTA hands the keys to the cross-shard merge
+    XShard xs{};
 };
 cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
@@ -57,7 +61,11 @@ cudaError_t launch_k1q_f32(const void* rows, int64_t n_rows, int ld, const float
 cudaError_t launch_select_segments(const uint64_t* base, int64_t seg_stride, int64_t q_stride, const int* counts,
                                    int64_t cnt_seg_stride, int64_t cnt_q_stride, int n_seg, int fixed_cnt, int seg_cap,
                                    const float* thr, int nq, int k, uint64_t* out, cudaStream_t st,
-                                   int64_t* ids = nullptr, float* scores = nullptr, int32_t* counts_out = nullptr);
+                                   int64_t* ids = nullptr, float* scores = nullptr, int32_t* counts_out = nullptr,
+                                   const XShard* xs = nullptr);
+// cross-shard finish as its own launch (paths whose keys are complete only after another kernel: K6, K8 remap):
+// local_keys [nq][k_local] sorted, 0-padded
+cudaError_t launch_xshard_finish(const XShard& xs, const uint64_t* local_keys, int nq, int k_local, cudaStream_t st);
 // keys [nq][k] → ids / scores / counts
 cudaError_t launch_decode(const uint64_t* keys, int nq, int k, int64_t* ids, float* scores,
                           int32_t* counts, cudaStream_t st);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "xshard.cuh"
 
 namespace yrb {
 
@@ -22,6 +23,8 @@ struct SelectArgs {
     int64_t* ids;                     // optional decoded outputs [nq][k] / [nq]
     float* scores;
     int32_t* out_counts;
+    int use_xs = 0;                   // sharded collection: hand the sorted keys to the cross-shard merge instead
+    XShard xs{};
 };
 
 __device__ __forceinline__ void select_emit(const SelectArgs& a, int q, int i, uint64_t key) {
@@ -194,6 +197,12 @@ __device__ __forceinline__ void select_topk_block(const SelectArgs& a, const int
             have = total < k ? total : k;
             seg = seg_end;
         }
+        if (a.use_xs) {
+            __syncthreads();
+            for (int i = tid; i < have; i += SEL_THREADS) sel[i] = sk[i];
+            xshard_finish(a.xs, q, sel, have, sk);
+            return;
+        }
         for (int i = tid; i < k; i += SEL_THREADS) select_emit(a, q, i, (i < have) ? sk[i] : 0ull);
         if (tid == 0 && a.out_counts) a.out_counts[q] = have;
         return;
@@ -284,6 +293,10 @@ __device__ __forceinline__ void select_topk_block(const SelectArgs& a, const int
     const int npow = next_pow2(nsel > 1 ? nsel : 2);
     for (int i = nsel + tid; i < npow; i += SEL_THREADS) sel[i] = 0ull;
     block_bitonic_desc(sel, npow, BetterU64());
+    if (a.use_xs) {
+        xshard_finish(a.xs, q, sel, nsel, sk);
+        return;
+    }
     for (int i = tid; i < k; i += SEL_THREADS) select_emit(a, q, i, (i < nsel) ? sel[i] : 0ull);
     if (tid == 0 && a.out_counts) a.out_counts[q] = nsel;
 }
