@@ -192,7 +192,49 @@ YRB_API int yrb_exchange_connect(yrb_exchange* ex, const unsigned char* all_hand
 YRB_API int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq, int k,
                                const int64_t* dev_row_base, int64_t* dev_out_ids, float* dev_out_scores,
                                int32_t* dev_out_counts, void* stream);
+/* One rank's whole sharded search through HOST buffers, enqueued from C on the index's stream: query upload, local
+ * scan + top-k, merge(), result in the caller's arrays (global ids).  Every rank calls it with the same queries;
+ * errors are reported through yrb_last_error(). */
+YRB_API int yrb_exchange_search(yrb_exchange* ex, yrb_index* ix, const float* queries, int nq, int k,
+                                const uint32_t* dev_mask, const int64_t* dev_row_base, int64_t* out_ids, float* out_scores,
+                                int32_t* out_counts);
 YRB_API int yrb_exchange_destroy(yrb_exchange* ex);
+
+/* ------------------------------------------------------------------ one collection over several GPUs, one process
+ * `VectorStoreFactory.create` hands out one store per collection inside the agents' single serving process
+ * (utu/rag/storage/base_storage.py:28-42, utu/rag/rag_tools/base_toolkit.py:79-91), so the multi-GPU form of the
+ * store is an object of that process too: n `yrb_index` shards, rows dealt block-cyclically (global row g lives in
+ * block g / block_rows on shard block % n), one worker thread per device, and the cross-GPU top-k merge folded
+ * into the kernel that finishes each query (NVLink peer stores + a ticket; the last shard to arrive merges and
+ * writes the result into pinned host memory).  Every entry mirrors its yrb_index_* namesake and works in GLOBAL row
+ * ids.  Peer access between the first device and the others is required (YRB_ERR_UNSUPPORTED otherwise). */
+typedef struct yrb_sharded yrb_sharded;
+YRB_API int yrb_sharded_create(yrb_sharded** out, const int* devices, int n_devices /* 1..8 */, int dim, int metric,
+                               int storage_dtype, int64_t reserve_rows, int block_rows /* 0 = 16384; power of two >= 64 */);
+YRB_API int yrb_sharded_destroy(yrb_sharded* sh);
+YRB_API int yrb_sharded_count(const yrb_sharded* sh, int64_t* out_rows, int64_t* out_live);
+YRB_API int yrb_sharded_info(const yrb_sharded* sh, int* out_dim, int* out_ld, int* out_metric, int* out_dtype,
+                             int* out_n_devices, int* out_block_rows, int64_t* out_capacity);
+/* shard s as a plain index (profiling, path forcing) and the device it lives on; do not append to it directly */
+YRB_API int yrb_sharded_shard(const yrb_sharded* sh, int s, yrb_index** out_index, int* out_device);
+YRB_API int yrb_sharded_append_host_f32(yrb_sharded* sh, const float* rows, int64_t n);
+/* rows resident on `src_device` (any device of the box; pieces for other shards travel over NVLink); the producer
+ * of dev_rows must have finished */
+YRB_API int yrb_sharded_append_device_f32(yrb_sharded* sh, const float* dev_rows, int64_t n, int src_device);
+YRB_API int yrb_sharded_read_rows(yrb_sharded* sh, const int64_t* row_ids, int64_t n, float* out_rows);
+YRB_API int yrb_sharded_read_raw(yrb_sharded* sh, int64_t row_begin, int64_t n, void* out_rows, float* out_sqnorm);
+YRB_API int yrb_sharded_append_raw(yrb_sharded* sh, const void* rows, const float* sqnorm, int64_t n);
+YRB_API int yrb_sharded_set_live(yrb_sharded* sh, const int64_t* row_ids, int64_t n, int live);
+YRB_API int yrb_sharded_truncate(yrb_sharded* sh, int64_t rows);
+YRB_API int yrb_sharded_clear(yrb_sharded* sh);
+YRB_API int yrb_sharded_column_write(yrb_sharded* sh, int col, int col_type, int64_t row_begin, int64_t n,
+                                     const void* values, const uint8_t* present);
+YRB_API int yrb_sharded_where(yrb_sharded* sh, const yrb_where* w, uint32_t* out_mask, int64_t* out_pass);
+YRB_API int yrb_sharded_search(yrb_sharded* sh, const float* queries, int nq, int k, const yrb_where* w,
+                               const uint32_t* mask, int64_t* out_ids, float* out_scores, int32_t* out_counts);
+YRB_API int yrb_sharded_search_multi(yrb_sharded* sh, const float* queries, int nq, int k, const yrb_where* const* wheres,
+                                     int64_t* out_ids, float* out_scores, int32_t* out_counts);
+YRB_API int yrb_sharded_stats(const yrb_sharded* sh, int64_t* out_kernel_launches, int64_t* out_searches);
 
 /* Force a kernel family for tests/bench: 0 auto, 1 K1 (GEMV + in-register top-k),
  * 2 K2 (tcgen05 GEMM + fused top-k epilogue), 3 K6 (key vector + radix select),

@@ -19,9 +19,8 @@
 #include <string>
 #include <vector>
 
-#include "../../include/yrb200.h"
+#include "index_internal.h"
 #include "common.cuh"
-#include "kernels.h"
 
 namespace yrb {
 
@@ -223,6 +222,43 @@ int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq,
     yrb::exchange_merge_kernel<<<nq, yrb::EX_THREADS, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return xfail(YRB_ERR_CUDA, std::string("exchange_merge_kernel: ") + cudaGetErrorString(e));
+    return YRB_OK;
+}
+
+// A whole sharded search of one rank through host buffers, enqueued from C on ONE stream: query upload, local scan +
+// top-k, the exchange/merge kernel writing the merged result into this rank's pinned result buffer (straight into host
+// memory when it is small), one synchronisation.  What `ShardedSearcher.search` used to assemble from torch calls
+// (60-90 us of Python per search at 8 GPUs).
+int yrb_exchange_search(yrb_exchange* ex, yrb_index* ix, const float* queries, int nq, int k, const uint32_t* dev_mask,
+                        const int64_t* dev_row_base, int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+    using namespace yrbi;
+    if (!ex || !ix || !queries || !dev_row_base || !out_ids || !out_scores) return fail(YRB_ERR_INVALID, "NULL argument");
+    if (nq < 1 || nq > ex->nq_cap || k < 1 || k > ex->k_cap) return fail(YRB_ERR_INVALID, "nq / k exceed the exchange's capacity");
+    if (ix->device != ex->device) return fail(YRB_ERR_INVALID, "index and exchange live on different devices");
+    if (k > ix->rows) return fail(YRB_ERR_INVALID, "k=%d exceeds this shard's rows=%lld", k, (long long)ix->rows);
+    std::lock_guard<std::mutex> g(ix->mu);
+    int rc = set_dev(ix);
+    if (rc) return rc;
+    if ((rc = ensure_scratch(ix, nq, k))) return rc;
+    cudaStream_t st = ix->stream;
+    memcpy(ix->h_q, queries, (size_t)nq * ix->dim * 4);
+    CK(cudaMemcpyAsync(ix->d_qf32, ix->h_q, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t* m = nullptr;
+    if ((rc = resolve_mask(ix, nullptr, dev_mask, &m, st, false))) return rc;
+    if ((rc = scan_select(ix, ix->d_qf32, nq, k, m, 0, ix->d_keys, nullptr, nullptr, nullptr, st))) return rc;
+    const size_t res_bytes = (size_t)nq * k * 12 + (size_t)nq * 4;
+    const bool zero_copy = ix->d_result_host && res_bytes <= 4096;
+    unsigned char* base = zero_copy ? ix->d_result_host : ix->d_result;
+    int64_t* d_ids = reinterpret_cast<int64_t*>(base);
+    float* d_scores = reinterpret_cast<float*>(base + (size_t)nq * k * 8);
+    int32_t* d_counts = reinterpret_cast<int32_t*>(base + (size_t)nq * k * 12);
+    if ((rc = yrb_exchange_merge(ex, ix->d_keys, nq, k, dev_row_base, d_ids, d_scores, d_counts, st))) return fail(rc, "%s", x_err.c_str());
+    ix->launches++;
+    if (!zero_copy) CK(cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_ids, ix->h_result, (size_t)nq * k * 8);
+    memcpy(out_scores, ix->h_result + (size_t)nq * k * 8, (size_t)nq * k * 4);
+    if (out_counts) memcpy(out_counts, ix->h_result + (size_t)nq * k * 12, (size_t)nq * 4);
     return YRB_OK;
 }
 

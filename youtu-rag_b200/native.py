@@ -34,8 +34,12 @@ EXPORTS = (
     "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_exchange_handle_bytes", "yrb_exchange_last_error", "yrb_exchange_create",
-    "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_set_reserved_sms", "yrb_index_stats", "yrb_index_profile",
+    "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_search", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_set_reserved_sms", "yrb_index_stats", "yrb_index_profile",
     "yrb_index_profile_read",
+    "yrb_sharded_create", "yrb_sharded_destroy", "yrb_sharded_count", "yrb_sharded_info", "yrb_sharded_shard",
+    "yrb_sharded_append_host_f32", "yrb_sharded_append_device_f32", "yrb_sharded_read_rows", "yrb_sharded_read_raw",
+    "yrb_sharded_append_raw", "yrb_sharded_set_live", "yrb_sharded_truncate", "yrb_sharded_clear",
+    "yrb_sharded_column_write", "yrb_sharded_where", "yrb_sharded_search", "yrb_sharded_search_multi", "yrb_sharded_stats",
 )
 
 
@@ -98,12 +102,31 @@ def lib() -> C.CDLL:
     L.yrb_exchange_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, vp]
     L.yrb_exchange_connect.argtypes = [vp, vp]
     L.yrb_exchange_merge.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.yrb_exchange_search.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]
     L.yrb_exchange_destroy.argtypes = [vp]
     L.yrb_index_set_path.argtypes = [vp, i32]
     L.yrb_index_set_reserved_sms.argtypes = [vp, i32]
     L.yrb_index_stats.argtypes = [vp, C.POINTER(i64)]
     L.yrb_index_profile.argtypes = [vp, i32]
     L.yrb_index_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.yrb_sharded_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, i32, i32, i64, i32]
+    L.yrb_sharded_destroy.argtypes = [vp]
+    L.yrb_sharded_count.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.yrb_sharded_info.argtypes = [vp] + [C.POINTER(i32)] * 6 + [C.POINTER(i64)]
+    L.yrb_sharded_shard.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i32)]
+    L.yrb_sharded_append_host_f32.argtypes = [vp, vp, i64]
+    L.yrb_sharded_append_device_f32.argtypes = [vp, vp, i64, i32]
+    L.yrb_sharded_read_rows.argtypes = [vp, vp, i64, vp]
+    L.yrb_sharded_read_raw.argtypes = [vp, i64, i64, vp, vp]
+    L.yrb_sharded_append_raw.argtypes = [vp, vp, vp, i64]
+    L.yrb_sharded_set_live.argtypes = [vp, vp, i64, i32]
+    L.yrb_sharded_truncate.argtypes = [vp, i64]
+    L.yrb_sharded_clear.argtypes = [vp]
+    L.yrb_sharded_column_write.argtypes = [vp, i32, i32, i64, i64, vp, vp]
+    L.yrb_sharded_where.argtypes = [vp, C.POINTER(Where), vp, C.POINTER(i64)]
+    L.yrb_sharded_search.argtypes = [vp, vp, i32, i32, C.POINTER(Where), vp, vp, vp, vp]
+    L.yrb_sharded_search_multi.argtypes = [vp, vp, i32, i32, C.POINTER(C.POINTER(Where)), vp, vp, vp]
+    L.yrb_sharded_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("yrb_last_error", "yrb_exchange_last_error"):
@@ -298,6 +321,159 @@ class Index:
         return n.value
 
 
+class ShardedIndex(Index):
+    """One collection row-sharded over several GPUs of the box, inside this process (opaque `yrb_sharded*`): same
+    methods as `Index`, global row ids, one worker thread per device, cross-GPU merge fused into the kernels
+    (csrc/sharded.cu, csrc/xshard.cuh).  `devices` may name a GPU twice (several shards on one GPU — tests)."""
+
+    def __init__(self, dim: int, metric: str = "cosine", dtype: str = "bf16", devices=(0,), reserve_rows: int = 0,
+                 block_rows: int = 0):
+        self._h = C.c_void_p()
+        self.devices = [int(d) for d in devices]
+        self.dim, self.metric, self.dtype, self.device = int(dim), metric, dtype, self.devices[0]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _ck(lib().yrb_sharded_create(C.byref(self._h), arr, len(self.devices), dim, METRICS[metric], DTYPES[dtype],
+                                     reserve_rows, block_rows))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            try:
+                _lib.yrb_sharded_destroy(self._h)
+            except Exception:  # noqa: BLE001
+                pass
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def reserve(self, rows: int) -> None:  # shards grow on demand
+        pass
+
+    def counts(self) -> tuple[int, int]:
+        r, l = C.c_int64(), C.c_int64()
+        _ck(lib().yrb_sharded_count(self._h, C.byref(r), C.byref(l)))
+        return r.value, l.value
+
+    def info(self) -> dict:
+        v = [C.c_int() for _ in range(6)]
+        cap = C.c_int64()
+        _ck(lib().yrb_sharded_info(self._h, *[C.byref(x) for x in v], C.byref(cap)))
+        return dict(dim=v[0].value, ld=v[1].value, metric=v[2].value, dtype=v[3].value, device=self.device,
+                    n_devices=v[4].value, block_rows=v[5].value, capacity=cap.value)
+
+    def shard(self, s: int) -> tuple[int, int]:
+        """(raw yrb_index* of shard s, its device) — for profiling / path forcing only."""
+        h, d = C.c_void_p(), C.c_int()
+        _ck(lib().yrb_sharded_shard(self._h, s, C.byref(h), C.byref(d)))
+        return h.value, d.value
+
+    def append(self, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"expected rows of shape [n, {self.dim}], got {rows.shape}")
+        _ck(lib().yrb_sharded_append_host_f32(self._h, rows.ctypes.data, rows.shape[0]))
+
+    def append_device(self, dev_ptr: int, n: int, stream: int = 0, src_device: int | None = None) -> None:
+        _ck(lib().yrb_sharded_append_device_f32(self._h, dev_ptr, n, self.device if src_device is None else src_device))
+
+    def read_rows(self, row_ids) -> np.ndarray:
+        ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+        out = np.empty((ids.shape[0], self.dim), dtype=np.float32)
+        _ck(lib().yrb_sharded_read_rows(self._h, ids.ctypes.data, ids.shape[0], out.ctypes.data))
+        return out
+
+    def read_raw(self, row_begin: int, n: int) -> tuple[np.ndarray, np.ndarray]:
+        ld = self.info()["ld"]
+        rows = np.empty((n, ld), dtype=np.uint16 if self.dtype == "bf16" else np.float32)
+        sq = np.empty(n, dtype=np.float32)
+        _ck(lib().yrb_sharded_read_raw(self._h, row_begin, n, rows.ctypes.data, sq.ctypes.data))
+        return rows, sq
+
+    def append_raw(self, rows: np.ndarray, sqnorm: np.ndarray) -> None:
+        ld = self.info()["ld"]
+        rows = np.ascontiguousarray(rows, dtype=np.uint16 if self.dtype == "bf16" else np.float32)
+        sqnorm = np.ascontiguousarray(sqnorm, dtype=np.float32)
+        if rows.ndim != 2 or rows.shape[1] != ld or sqnorm.shape[0] != rows.shape[0]:
+            raise ValueError(f"expected raw rows [n, {ld}] and n squared norms")
+        _ck(lib().yrb_sharded_append_raw(self._h, rows.ctypes.data, sqnorm.ctypes.data, rows.shape[0]))
+
+    def set_live(self, row_ids, live: bool) -> None:
+        ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+        _ck(lib().yrb_sharded_set_live(self._h, ids.ctypes.data, ids.shape[0], int(bool(live))))
+
+    def clear(self) -> None:
+        _ck(lib().yrb_sharded_clear(self._h))
+
+    def truncate(self, rows: int) -> None:
+        _ck(lib().yrb_sharded_truncate(self._h, rows))
+
+    def column_write(self, col: int, col_type: int, row_begin: int, values: np.ndarray, present: np.ndarray) -> None:
+        dt = {COL_I64: np.int64, COL_F64: np.float64, COL_CODE: np.int32, COL_BOOL: np.uint8}[col_type]
+        values = np.ascontiguousarray(values, dtype=dt)
+        present = np.ascontiguousarray(present, dtype=np.uint8)
+        assert values.shape[0] == present.shape[0]
+        _ck(lib().yrb_sharded_column_write(self._h, col, col_type, row_begin, values.shape[0], values.ctypes.data,
+                                           present.ctypes.data))
+
+    def where_mask(self, where: CompiledWhere | None) -> tuple[np.ndarray, int]:
+        out = np.zeros((self.rows + 31) // 32, dtype=np.uint32)
+        n = C.c_int64()
+        _ck(lib().yrb_sharded_where(self._h, C.byref(where.struct) if where else None, out.ctypes.data, C.byref(n)))
+        return out, n.value
+
+    def search(self, queries: np.ndarray, k: int, where: CompiledWhere | None = None,
+               mask: np.ndarray | None = None, wheres: list | None = None):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected queries of shape [nq, {self.dim}], got {q.shape}")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        if wheres is not None:
+            if where is not None or mask is not None:
+                raise ValueError("pass either a shared filter (where/mask) or per-query filters (wheres)")
+            if len(wheres) != nq:
+                raise ValueError(f"expected {nq} per-query filters, got {len(wheres)}")
+            arr = (C.POINTER(Where) * nq)(*[C.pointer(w.struct) if w is not None else C.POINTER(Where)() for w in wheres])
+            _ck(lib().yrb_sharded_search_multi(self._h, q.ctypes.data, nq, k, arr, ids.ctypes.data, scores.ctypes.data,
+                                               counts.ctypes.data))
+            return ids, scores, counts
+        mptr = None
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, dtype=np.uint32)
+            if mask.shape[0] < (self.rows + 31) // 32:
+                raise ValueError("mask has fewer than ceil(rows/32) words")
+            mptr = mask.ctypes.data
+        _ck(lib().yrb_sharded_search(self._h, q.ctypes.data, nq, k, C.byref(where.struct) if where else None, mptr,
+                                     ids.ctypes.data, scores.ctypes.data, counts.ctypes.data))
+        return ids, scores, counts
+
+    def _each_shard(self, fn_name: str, *args) -> None:
+        for s in range(len(self.devices)):
+            _ck(getattr(lib(), fn_name)(C.c_void_p(self.shard(s)[0]), *args))
+
+    def set_path(self, path: int) -> None:
+        self._each_shard("yrb_index_set_path", path)
+
+    def profile(self, enable: bool) -> None:
+        self._each_shard("yrb_index_profile", int(enable))
+
+    def set_reserved_sms(self, n: int) -> None:
+        self._each_shard("yrb_index_set_reserved_sms", n)
+
+    def launches(self) -> int:
+        n, m = C.c_int64(), C.c_int64()
+        _ck(lib().yrb_sharded_stats(self._h, C.byref(n), C.byref(m)))
+        return n.value
+
+    def search_device(self, *a, **k):
+        raise NativeError(-4, "a sharded index answers through host buffers (the merged result lands in pinned host memory)")
+
+    search_device_ids = search_device
+
+
 def merge_topk_device(device: int, dev_keys: int, parts: int, nq: int, k: int, dev_row_base: int, dev_ids: int,
                       dev_scores: int, dev_counts: int, stream: int = 0) -> None:
     _ck(lib().yrb_merge_topk_device(device, dev_keys, parts, nq, k, dev_row_base, dev_ids, dev_scores,
@@ -329,6 +505,19 @@ class Exchange:
               dev_counts: int, stream: int = 0) -> None:
         self._ckx(lib().yrb_exchange_merge(self._h, dev_local_keys, nq, k, dev_row_base, dev_ids, dev_scores,
                                            dev_counts or None, stream or None))
+
+    def search(self, index: "Index", queries: np.ndarray, k: int, dev_mask: int, dev_row_base: int):
+        """This rank's whole sharded search through host buffers, enqueued from C (yrb_exchange_search)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        scores = np.empty((nq, k), dtype=np.float32)
+        counts = np.empty(nq, dtype=np.int32)
+        _ck(lib().yrb_exchange_search(self._h, index._h, q.ctypes.data, nq, k, dev_mask or None, dev_row_base,
+                                      ids.ctypes.data, scores.ctypes.data, counts.ctypes.data))
+        return ids, scores, counts
 
     def close(self) -> None:
         if getattr(self, "_h", None) and self._h.value:

@@ -144,6 +144,11 @@ class ShardedSearcher:
         if q.ndim == 1:
             q = q[None, :]
         nq = q.shape[0]
+        if self.exchange is not None and nq <= self.exchange.nq_cap and k <= self.exchange.k_cap:
+            # the whole search is enqueued from C on one stream (yrb_exchange_search): no torch calls per search
+            self.synchronize()   # earlier search_device() calls share the index's scratch
+            return self.exchange.search(self.index, q, k, dev_mask.data_ptr() if dev_mask is not None else 0,
+                                        self._base_dev.data_ptr())
         slots = self._buffers(nq, k)
         stage = self._hq.get(nq)
         if stage is None:

@@ -47,6 +47,11 @@ class B200VectorStore(BaseVectorStore):
         if self._dtype not in native.DTYPES:
             raise ValueError(f"index_params.storage_dtype must be one of {sorted(native.DTYPES)}, got {self._dtype!r}")
         self._device = int(p.get("device", 0))
+        # index_params.devices = [0, 1, …]: the collection is row-sharded over these GPUs of the box inside this
+        # process (native.ShardedIndex); absent or a single entry → one GPU
+        devs = p.get("devices")
+        self._devices = [int(d) for d in devs] if devs else None
+        self._block_rows = int(p.get("shard_block_rows", 0))
         self._reserve = int(p.get("reserve_rows", 0))
         self._include_embeddings = bool(p.get("include_embeddings", False))
         # unknown metric names fall back to cosine like chroma_store.py:52
@@ -71,7 +76,11 @@ class B200VectorStore(BaseVectorStore):
     # ------------------------------------------------------------------ helpers
     def _ensure_index(self, dim: int) -> native.Index:
         if self._index is None:
-            self._index = native.Index(dim, self._metric, self._dtype, self._device, self._reserve)
+            if self._devices and len(self._devices) > 1:
+                self._index = native.ShardedIndex(dim, self._metric, self._dtype, self._devices, self._reserve, self._block_rows)
+            else:
+                dev = self._devices[0] if self._devices else self._device
+                self._index = native.Index(dim, self._metric, self._dtype, dev, self._reserve)
         elif self._index.dim != dim:
             raise ValueError(f"Embedding dimension {dim} does not match collection dimensionality {self._index.dim}")
         return self._index
