@@ -10,7 +10,7 @@ The producer methods are taken UNMODIFIED (source text, via ast) from
 and executed here on representative arguments (the modules themselves do not import in this container: agents SDK,
 hydra, chromadb are missing, so the functions are exec'd in a bare namespace; `search_memories` is run with a stub
 `self` whose `search` records the filters it is handed).  The fixture pins the dicts; their evaluation over the
-sample metadata is recorded from oracle/where_eval.py (Chroma itself is not installable: "unpinned").
+sample metadata is recorded from the golden fake engine's own matcher (make_golden.chroma_where) (Chroma itself is not installable: "unpinned").
 
 Usage: python tests/golden/make_filter_golden.py     (only where /root/reference exists)
 """
@@ -32,7 +32,8 @@ REF = Path("/root/reference")
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent.parent))
 
-from oracle import where_eval  # noqa: E402  (test infrastructure)
+sys.path.insert(0, str(HERE))
+from make_golden import chroma_where  # noqa: E402  (the fake engine's own matcher: independent of oracle/where_eval.py)
 
 
 def method_source(path: Path, cls: str, name: str) -> str:
@@ -151,7 +152,7 @@ def run():
 
     metas = sample_metadata()
     for c in cases:
-        c["rows"] = None if c["where"] is None else np.flatnonzero(where_eval.eval_where(c["where"], metas)).tolist()
+        c["rows"] = None if c["where"] is None else np.flatnonzero(chroma_where(c["where"], metas)).tolist()
     out = {"metadatas": metas, "cases": cases}
     (HERE / "filter_producers.json").write_text(json.dumps(out, ensure_ascii=False, separators=(",", ":")))
     print("wrote", HERE / "filter_producers.json", len(cases), "cases;",

@@ -9,7 +9,8 @@ Runs only where /root/reference exists (never on the GPU box).  What it pins, an
   FAISS's normalise/score/post-filter logic (faiss_store.py:143-199) and the retriever's
   threshold / rank / slice rules (base_retriever.py:53-80).
 * The engines underneath (chromadb 1.3.4 HNSW, faiss-cpu 1.12.0) are NOT installable here, so
-  `chromadb` and `faiss` are replaced by minimal exact fakes defined in this file.  The numbers in
+  `chromadb` and `faiss` are replaced by minimal exact fakes defined in this file (with their OWN `where` matcher,
+  `chroma_where` below — not the oracle's: the fixtures are independent of oracle/where_eval.py).  The numbers in
   the fixtures therefore pin the reference's Python semantics, not the engines' arithmetic:
   parity stays "unpinned" for the latter.
 
@@ -32,7 +33,88 @@ REF = Path("/root/reference")
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE.parent.parent))
 
-from oracle import where_eval  # noqa: E402  (test infrastructure)
+
+
+# ----------------------------------------------------------------------------- the fake engine's own `where` matcher
+# Written here from Chroma's documented `where` grammar, deliberately sharing NO code with oracle/where_eval.py
+# (fixtures produced through the oracle's matcher cannot disagree with the oracle).  One metadata dict at
+# a time, recursive, types compared by Python type name.  The decisions it restates are DESIGN.md §5's.
+_W_LOGICAL = ("$and", "$or")
+_W_COMPARE = ("$gt", "$gte", "$lt", "$lte")
+_W_ALL = _W_COMPARE + ("$eq", "$ne", "$in", "$nin")
+
+
+def _w_kind(v):
+    return "bool" if isinstance(v, bool) else "int" if isinstance(v, int) else "float" if isinstance(v, float) else \
+        "str" if isinstance(v, str) else None
+
+
+def _w_check(where):
+    """Raise ValueError where chromadb's validate_where would."""
+    if not isinstance(where, dict) or len(where) != 1:
+        raise ValueError(f"Expected where to have exactly one operator, got {where}")
+    (key, val), = where.items()
+    if not isinstance(key, str):
+        raise ValueError(f"Expected where key to be a str, got {key}")
+    if key in _W_LOGICAL:
+        if not isinstance(val, list) or len(val) < 2:
+            raise ValueError(f"Expected where value for {key} to be a list with at least two where expressions, got {val}")
+        for child in val:
+            _w_check(child)
+        return
+    if key.startswith("$"):
+        raise ValueError(f"Expected where to have a field name or one of {_W_LOGICAL}, got {key}")
+    if not isinstance(val, dict):
+        if _w_kind(val) is None:
+            raise ValueError(f"Expected where value to be a str, int, float, bool or operator expression, got {val}")
+        return
+    if len(val) != 1:
+        raise ValueError(f"Expected operator expression to have exactly one operator, got {val}")
+    (op, operand), = val.items()
+    if op not in _W_ALL:
+        raise ValueError(f"Expected where operator to be one of {_W_ALL}, got {op}")
+    if op in _W_COMPARE:
+        if _w_kind(operand) not in ("int", "float"):
+            raise ValueError(f"Expected operand value to be an int or a float for operator {op}, got {operand}")
+    elif op in ("$in", "$nin"):
+        if not isinstance(operand, list) or not operand:
+            raise ValueError(f"Expected where operand value to be a non-empty list, got {operand}")
+        kinds = {_w_kind(x) for x in operand}
+        if None in kinds or len(kinds) != 1:
+            raise ValueError(f"Expected where operand value to be a list of one of str, int, float or bool, got {operand}")
+    elif _w_kind(operand) is None:
+        raise ValueError(f"Expected where operand value to be a str, int, float or bool, got {operand}")
+
+
+def _w_row(where, meta):
+    (key, val), = where.items()
+    if key == "$and":
+        return all(_w_row(c, meta) for c in val)
+    if key == "$or":
+        return any(_w_row(c, meta) for c in val)
+    op, operand = next(iter(val.items())) if isinstance(val, dict) else ("$eq", val)
+    probe = operand[0] if op in ("$in", "$nin") else operand
+    stored = meta.get(key)
+    typed = key in meta and _w_kind(stored) == _w_kind(probe)      # a value of another type is invisible to the operand
+    if op == "$eq":
+        return typed and stored == operand
+    if op == "$ne":
+        return not (typed and stored == operand)
+    if op == "$in":
+        return typed and stored in operand
+    if op == "$nin":
+        return not (typed and stored in operand)
+    if not typed:
+        return False
+    return {"$gt": stored > operand, "$gte": stored >= operand, "$lt": stored < operand, "$lte": stored <= operand}[op]
+
+
+def chroma_where(where, metas):
+    """bool[len(metas)]: rows a chromadb `where` selects (None selects all)."""
+    if where is None:
+        return np.ones(len(metas), bool)
+    _w_check(where)
+    return np.fromiter((_w_row(where, m) for m in metas), bool, count=len(metas))
 
 
 # ----------------------------------------------------------------------------- fake engines
@@ -75,7 +157,7 @@ class _FakeCollection:
         self.last_where = where
         out = {"ids": [], "documents": [], "metadatas": [], "embeddings": [], "distances": []}
         for q in query_embeddings:
-            keep = where_eval.eval_where(where, self.metas) if self.ids else np.zeros(0, bool)
+            keep = chroma_where(where, self.metas) if self.ids else np.zeros(0, bool)
             idx = np.flatnonzero(keep)
             if idx.size:
                 d = self._dist(q)[idx]
@@ -94,7 +176,7 @@ class _FakeCollection:
         if ids is not None:
             sel = [self.ids.index(i) for i in ids if i in self.ids]
         else:
-            sel = np.flatnonzero(where_eval.eval_where(where, self.metas)).tolist() if self.ids else []
+            sel = np.flatnonzero(chroma_where(where, self.metas)).tolist() if self.ids else []
         return {"ids": [self.ids[i] for i in sel], "documents": [self.docs[i] for i in sel],
                 "metadatas": [dict(self.metas[i]) for i in sel], "embeddings": [self.emb[i].tolist() for i in sel]}
 

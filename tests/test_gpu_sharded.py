@@ -98,6 +98,30 @@ def test_row_map_residency_roundtrip(dtype):
             o.close()
 
 
+def test_device_side_appends_cross_gpus():
+    """Rows generated on one GPU and appended with append_device: pieces for other shards travel over NVLink and
+    must be ingested only after they have landed (bench.py's sharded-store leg builds its corpus this way)."""
+    import torch
+
+    n, d, block = 200_000, 256, 1024
+    for devs in device_sets():
+        ix = native.ShardedIndex(d, "cosine", "bf16", devs, block_rows=block)
+        single = native.Index(d, "cosine", "bf16", devs[0], n)
+        gen = torch.Generator(device=f"cuda:{devs[0]}")
+        for b in range(0, n, 50_000):
+            gen.manual_seed(b)
+            blk = torch.randn(50_000, d, device=f"cuda:{devs[0]}", generator=gen)
+            torch.cuda.synchronize()
+            ix.append_device(blk.data_ptr(), 50_000, src_device=devs[0])
+            single.append_device(blk.data_ptr(), 50_000)
+        a, sa = ix.read_raw(0, n)
+        b_, sb = single.read_raw(0, n)
+        np.testing.assert_array_equal(a, b_)
+        np.testing.assert_array_equal(sa, sb)
+        ix.close()
+        single.close()
+
+
 def _check(ix, rows_stored, q, k, metric, dtype, oracle_mask=None, **kw):
     ids, scores, counts = ix.search(q, k, **kw)
     qq = np.atleast_2d(q)

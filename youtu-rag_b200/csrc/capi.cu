@@ -35,6 +35,23 @@ void set_error(const std::string& m) { g_err = m; }
 
 int col_width(int t) { return t == YRB_COL_I64 || t == YRB_COL_F64 ? 8 : (t == YRB_COL_CODE ? 4 : 1); }
 
+DevicePool* device_pool(int device) {
+    static std::mutex reg_mu;
+    static std::map<int, DevicePool*> reg;
+    std::lock_guard<std::mutex> g(reg_mu);
+    auto it = reg.find(device);
+    if (it != reg.end()) return it->second;
+    DevicePool* p = new DevicePool();
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete p;
+        return nullptr;
+    }
+    p->k2 = yrb::k2_create();
+    reg[device] = p;
+    return p;
+}
+
 }  // namespace yrbi
 
 using namespace yrbi;
@@ -62,7 +79,7 @@ int regrow(T** p, size_t old_bytes, size_t new_bytes, bool zero_tail, cudaStream
 int ensure_capacity(yrb_index* ix, int64_t want) {
     if (want <= ix->capacity) return YRB_OK;
     int64_t cap = std::max<int64_t>(want, ix->capacity + ix->capacity / 2);
-    cap = std::max<int64_t>(cap, 1024);
+    cap = std::max<int64_t>(cap, 256);   // tiny collections (per-user memories) stay tiny: 512 KiB of rows at 1024-d
     cap = (cap + 255) / 256 * 256;
     const size_t es = yrb::elem_size(ix->dtype);
     int rc;
@@ -231,6 +248,7 @@ int build_prog(yrb_index* ix, const yrb_where* w) {
 // evaluates w (and/or ANDs a device mask) into ix->d_mask; returns the mask pointer to scan with
 int resolve_mask(yrb_index* ix, const yrb_where* w, const uint32_t* dev_extra, const uint32_t** out, cudaStream_t st,
                  bool count) {
+    Nvtx nvtx_("k4_filter");
     const uint32_t* live = ix->n_dead > 0 ? ix->d_live : nullptr;
     if (w) {
         int rc = build_prog(ix, w);
@@ -354,6 +372,7 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
 // K1 prepares the query in its own prologue; K2 needs the prepared bf16 matrix (K5 launch).
 int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, int64_t mask_q_stride,
                 uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st, const yrb::XShard* xs) {
+    Nvtx nvtx_("scan_select");
     if (xs) ids = nullptr, scores = nullptr, counts = nullptr;  // the cross-shard merge writes the results
     const bool decode = ids != nullptr;
     const int sms = std::max(2, ix->sm_count - ix->reserved_sms) & ~1;  // even: K2 runs CTA clusters of 2
@@ -370,6 +389,9 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
     if ((path == 1 || path == 2) && k > YRB_FUSED_K_MAX)
         return fail(YRB_ERR_UNSUPPORTED, "fused selection handles k <= %d", YRB_FUSED_K_MAX);
     if (path == 2) {
+        // the K2 buffers may be shared by every index of this device: one enqueue sequence at a time
+        std::unique_lock<std::mutex> pool_lock;
+        if (ix->pool) pool_lock = std::unique_lock<std::mutex>(ix->pool->mu);
         // K8: a filter shared by the batch that passes at most a quarter of the rows → gather the passing rows
         // and run the GEMM on the compact matrix (needs the pass count on the host: one stream synchronisation)
         const void* k2_rows = ix->d_rows;
@@ -489,21 +511,23 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             }
             int rc = prof_mark(ix, st);
             if (rc) return rc;
+            int lists = parts;
             CK(yrb::launch_k1(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
-                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, k, pk, ix->d_ticket, o, &fused, sms, st));
+                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, k, pk, ix->d_ticket, o, &fused, sms, st,
+                              &lists));
             if ((rc = prof_mark(ix, st))) return rc;
             ix->launches++;
             if (trace) {  // debug aid: phase breakdown of this launch on stderr (µs relative to the first CTA's start)
-                std::vector<unsigned long long> h((size_t)(parts + 2) * 8);
+                std::vector<unsigned long long> h((size_t)(lists + 2) * 8);
                 CK(cudaStreamSynchronize(st));
                 CK(cudaMemcpy(h.data(), ix->d_k1trace, h.size() * 8, cudaMemcpyDeviceToHost));
                 unsigned long long t0 = ~0ull;
-                for (int c = 0; c < parts; ++c) t0 = std::min(t0, h[(size_t)c * 8]);
+                for (int c = 0; c < lists; ++c) t0 = std::min(t0, h[(size_t)c * 8]);
                 const char* names[8] = {"start", "prep_done", "scan_done", "cta_merge_done", "ticket_done", "final_done", "warp0_scan_done", "first_group_done"};
                 for (int ph = 0; ph < 8; ++ph) {
                     double lo = 1e30, hi = -1e30, sum = 0;
                     int n = 0;
-                    for (int c = 0; c < parts; ++c) {
+                    for (int c = 0; c < lists; ++c) {
                         const unsigned long long t = h[(size_t)c * 8 + ph];
                         if (!t) continue;
                         const double us = (double)(t - t0) * 1e-3;
@@ -514,7 +538,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
                     }
                     if (n) fprintf(stderr, "[k1trace] %-16s n=%3d min %8.2f avg %8.2f max %8.2f us\n", names[ph], n, lo, sum / n, hi);
                 }
-                const unsigned long long* f = h.data() + (size_t)parts * 8;  // the last CTA's final merge
+                const unsigned long long* f = h.data() + (size_t)lists * 8;  // the last CTA's final merge
                 const unsigned long long* c0 = f + 8;  // CTA 0's own merge
                 if (c0[0])
                     fprintf(stderr, "[k1trace] cta0 merge:  begin %.2f init %.2f bound %.2f ranked %.2f (survivors %llu) emitted %.2f us\n",
@@ -524,7 +548,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
                             (f[0] - t0) * 1e-3, (f[1] - t0) * 1e-3, (f[2] - t0) * 1e-3, (f[3] - t0) * 1e-3, f[6], (f[4] - t0) * 1e-3);
             }
             if (!fused) {
-                CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, parts, k, k, nullptr, 1, k, o.final_keys, st, o.ids,
+                CK(yrb::launch_select_segments(pk, k, 0, nullptr, 0, 0, lists, k, k, nullptr, 1, k, o.final_keys, st, o.ids,
                                                o.scores, o.count, xs ? &xj : nullptr));
                 ix->launches++;
             }
@@ -664,14 +688,24 @@ int yrb_index_create(yrb_index** out, int device, int dim, int metric, int stora
     } while (0)
     CKB(cudaSetDevice(device));
     CKB(cudaDeviceGetAttribute(&ix->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CKB(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    {
+        static const bool private_streams = getenv("YRB_PRIVATE_STREAMS") && getenv("YRB_PRIVATE_STREAMS")[0] == '1';
+        if (!private_streams) {
+            ix->pool = device_pool(device);
+            if (!ix->pool) return bail(fail(YRB_ERR_CUDA, "cannot create the stream of device %d", device));
+            ix->stream = ix->pool->stream;
+            ix->k2 = ix->pool->k2;
+        } else {
+            CKB(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+            ix->k2 = yrb::k2_create();
+        }
+    }
     CKB(cudaMalloc(&ix->d_prog, sizeof(yrb::WhereProgDev)));
     CKB(cudaMallocHost(&ix->h_prog, sizeof(yrb::WhereProgDev)));
     CKB(cudaMalloc(&ix->d_pass, 8));
     CKB(cudaMalloc(&ix->d_ticket, 8));  // [0] CTAs done, [1] next chunk
     CKB(cudaMemset(ix->d_ticket, 0, 8));
 #undef CKB
-    ix->k2 = yrb::k2_create();
     rc = ensure_capacity(ix, std::max<int64_t>(reserve_rows, 1));
     if (rc) return bail(rc);
     *out = ix;
@@ -704,13 +738,14 @@ int yrb_index_destroy(yrb_index* ix) {
     FREE_HOST(ix->h_pass);
     FREE_HOST(ix->h_prog);
     FREE_HOST(ix->h_stage);
+    FREE_DEV(ix->d_append);
     for (auto& kv : ix->cols) {
         FREE_DEV(kv.second.values);
         FREE_DEV(kv.second.present);
     }
-    if (ix->k2) yrb::k2_destroy(ix->k2);
+    if (ix->k2 && !ix->pool) yrb::k2_destroy(ix->k2);
     for (cudaEvent_t e : ix->prof_ev) cudaEventDestroy(e);
-    if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->stream && !ix->pool) cudaStreamDestroy(ix->stream);
     delete ix;
     return YRB_OK;
 }
@@ -743,6 +778,7 @@ int yrb_index_info(const yrb_index* ix, int* out_dim, int* out_ld, int* out_metr
 }
 
 int yrb_index_append_host_f32(yrb_index* ix, const float* rows, int64_t n) {
+    Nvtx nvtx_("yrb_index_append_host_f32");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && !rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
     if (n == 0) return YRB_OK;
@@ -754,27 +790,24 @@ int yrb_index_append_host_f32(yrb_index* ix, const float* rows, int64_t n) {
     // staged in chunks: pageable → pinned → device fp32 scratch → K5 into place
     const int64_t chunk = std::max<int64_t>(1, (int64_t)(32u << 20) / ((int64_t)ix->dim * 4));
     if ((rc = ensure_stage(ix, (size_t)chunk * ix->dim * 4))) return rc;
-    float* d_tmp = nullptr;
-    CK(cudaMalloc(&d_tmp, (size_t)chunk * ix->dim * 4));
+    const size_t need = (size_t)std::min<int64_t>(chunk, n) * ix->dim * 4;
+    if (need > ix->append_bytes) {
+        FREE_DEV(ix->d_append);
+        ix->append_bytes = 0;
+        CK(cudaMalloc(&ix->d_append, need));
+        ix->append_bytes = need;
+    }
     for (int64_t r = 0; r < n; r += chunk) {
         const int64_t m = std::min(chunk, n - r);
         memcpy(ix->h_stage, rows + r * ix->dim, (size_t)m * ix->dim * 4);
-        cudaError_t e = cudaMemcpyAsync(d_tmp, ix->h_stage, (size_t)m * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream);
-        if (e == cudaSuccess) {
-            rc = append_device_locked(ix, d_tmp, m, ix->stream);
-        } else {
-            rc = fail(YRB_ERR_CUDA, "H2D copy of rows failed: %s", cudaGetErrorString(e));
-        }
-        if (rc) {
-            cudaFree(d_tmp);
-            return rc;
-        }
+        CK(cudaMemcpyAsync(ix->d_append, ix->h_stage, (size_t)m * ix->dim * 4, cudaMemcpyHostToDevice, ix->stream));
+        if ((rc = append_device_locked(ix, ix->d_append, m, ix->stream))) return rc;
     }
-    CK(cudaFree(d_tmp));
     return YRB_OK;
 }
 
 int yrb_index_append_device_f32(yrb_index* ix, const float* dev_rows, int64_t n, void* stream) {
+    Nvtx nvtx_("yrb_index_append_device_f32");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && !dev_rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
     if (n == 0) return YRB_OK;
@@ -958,6 +991,7 @@ int yrb_index_column_write(yrb_index* ix, int col, int col_type, int64_t row_beg
 }
 
 int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64_t* out_pass) {
+    Nvtx nvtx_("yrb_index_where");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
     int rc = set_dev(ix);
@@ -981,6 +1015,7 @@ int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64
 static int search_host(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w,
                        const yrb_where* const* per_query, const uint32_t* mask, int64_t* out_ids, float* out_scores,
                        int32_t* out_counts) {
+    Nvtx nvtx_("yrb_index_search");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (nq < 1 || !queries) return fail(YRB_ERR_INVALID, "need at least one query");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
@@ -1033,6 +1068,12 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     const int64_t* h_ids = reinterpret_cast<const int64_t*>(ix->h_result);
     const float* h_scores = reinterpret_cast<const float*>(ix->h_result + (size_t)nq * ke * 8);
     const int32_t* h_counts = reinterpret_cast<const int32_t*>(ix->h_result + (size_t)nq * ke * 12);
+    if (ke == k) {  // the usual case: the packed result has the caller's layout
+        memcpy(out_ids, h_ids, (size_t)nq * k * 8);
+        memcpy(out_scores, h_scores, (size_t)nq * k * 4);
+        if (out_counts) memcpy(out_counts, h_counts, (size_t)nq * 4);
+        return YRB_OK;
+    }
     for (int q = 0; q < nq; ++q) {
         for (int j = 0; j < k; ++j) {
             const bool ok = j < ke;
@@ -1057,6 +1098,7 @@ int yrb_index_search_multi(yrb_index* ix, const float* queries, int nq, int k, c
 
 int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k, const uint32_t* dev_mask,
                             uint64_t* dev_out_keys, void* stream) {
+    Nvtx nvtx_("yrb_index_search_device");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (nq < 1 || !dev_queries || !dev_out_keys) return fail(YRB_ERR_INVALID, "bad arguments");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
@@ -1077,6 +1119,7 @@ int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int
 
 int yrb_index_search_device_ids(yrb_index* ix, const float* dev_queries, int nq, int k, const uint32_t* dev_mask,
                                 int64_t* dev_out_ids, float* dev_out_scores, int32_t* dev_out_counts, void* stream) {
+    Nvtx nvtx_("yrb_index_search_device_ids");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (nq < 1 || !dev_queries || !dev_out_ids || !dev_out_scores || !dev_out_counts)
         return fail(YRB_ERR_INVALID, "bad arguments");

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <map>
 #include <mutex>
@@ -15,6 +16,15 @@
 #include "xshard.cuh"
 
 namespace yrbi {
+
+// NVTX range around an ABI entry or a phase of a search (nsys timelines of the sharded path read as
+// entry → filter → scan → merge).  Header-only NVTX v3: no cost unless a profiler is attached.
+struct Nvtx {
+    explicit Nvtx(const char* name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+    Nvtx(const Nvtx&) = delete;
+    Nvtx& operator=(const Nvtx&) = delete;
+};
 
 // sets the calling thread's error message (yrb_last_error) and returns `code`
 int fail(int code, const char* fmt, ...);
@@ -29,6 +39,17 @@ struct Column {
 };
 
 inline int64_t mask_words(int64_t rows) { return (((rows + 31) / 32) + 1) & ~int64_t(1); }
+
+// What every index on one GPU shares (an agent process holds one index per collection / per user
+// memory, and round 1 gave each its own stream and 86 MB of K2 candidate buffers): ONE stream — so the searches of a
+// device are ordered and may share scratch — and ONE set of K2 buffers.  Enqueue sequences that use the shared K2
+// state hold `mu`.  Lives as long as the process.  YRB_PRIVATE_STREAMS=1 restores one stream + K2 state per index.
+struct DevicePool {
+    cudaStream_t stream = nullptr;
+    yrb::K2State* k2 = nullptr;
+    std::mutex mu;
+};
+DevicePool* device_pool(int device);   // NULL if the stream cannot be created
 
 }  // namespace yrbi
 
@@ -91,7 +112,10 @@ struct yrb_index {
     unsigned char* h_result = nullptr;
     void* h_stage = nullptr;
     size_t stage_bytes = 0;
+    float* d_append = nullptr;  // device staging of append_host_f32 (grow-only; round 1 allocated it per call)
+    size_t append_bytes = 0;
     yrb::K2State* k2 = nullptr;
+    yrbi::DevicePool* pool = nullptr;   // non-NULL: stream and k2 belong to the device pool
     int path = 0;
     int reserved_sms = 0;
     int64_t launches = 0;

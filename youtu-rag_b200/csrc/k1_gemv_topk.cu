@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -73,26 +74,50 @@ __device__ __forceinline__ float prepare_query(const float* __restrict__ q_raw, 
     constexpr int H = F32 ? 1 : 2;
     constexpr int EPL = F32 ? 4 : 8;
     const int lane = threadIdx.x & 31;
+    // K5 has two forms (k5_ingest.cu): the streaming one adds a lane's squares float4 by float4, the generic one
+    // element by element; follow whichever K5 would take for this query so that both kernels see the same bits
+    const bool vec = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(q_raw) & 15) == 0) && ((ld + 127) / 128 <= 16);
     double ss = 0.0;
     if (normalize) {
-        for (int i = lane; i < dim; i += 32) {
-            const double v = (double)q_raw[i];
-            ss += v * v;
+        if (vec) {
+            const float4* q4 = reinterpret_cast<const float4*>(q_raw);
+            for (int j = lane; j < (dim >> 2); j += 32) {
+                const float4 v = q4[j];
+                ss += (double)v.x * (double)v.x;
+                ss += (double)v.y * (double)v.y;
+                ss += (double)v.z * (double)v.z;
+                ss += (double)v.w * (double)v.w;
+            }
+        } else {
+            for (int i = lane; i < dim; i += 32) {
+                const double v = (double)q_raw[i];
+                ss += v * v;
+            }
         }
         ss = warp_sum(ss);
     }
     const bool scale = normalize && ss > 0.0;
-    const double nrm = scale ? sqrt(ss) : 1.0;
+    const double inv = scale ? 1.0 / sqrt(ss) : 1.0;   // K5's arithmetic: multiply by the fp64 reciprocal of the norm
     auto stored = [&](int e) -> float {
         float y = 0.f;
-        if (e < dim) y = scale ? (float)((double)q_raw[e] / nrm) : q_raw[e];
+        if (e < dim) y = scale ? (float)((double)q_raw[e] * inv) : q_raw[e];
         return F32 ? y : __bfloat162float(__float2bfloat16_rn(y));
     };
     float sqn = 0.f;
     if (want_sq) {
-        for (int i = lane; i < ld; i += 32) {
-            const float y = stored(i);
-            sqn = fmaf(y, y, sqn);
+        if (vec) {
+            for (int j = lane; j < (ld >> 2); j += 32) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float y = stored(4 * j + c);
+                    sqn = fmaf(y, y, sqn);
+                }
+            }
+        } else {
+            for (int i = lane; i < ld; i += 32) {
+                const float y = stored(i);
+                sqn = fmaf(y, y, sqn);
+            }
         }
         sqn = warp_sum(sqn);
     }
@@ -685,12 +710,16 @@ static cudaError_t k1_launch_t(const void* rows, int64_t n_rows, int dim, int ld
 
 cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
-                      unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st) {
+                      unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st, int* parts_out) {
     if (k < 1 || k > 128) return cudaErrorInvalidValue;
     static_assert(K1_THREADS == SEL_THREADS, "the fused selection runs on the scan's CTA");
     const int ld16 = ld * elem_size(dtype) / 16;
     const int nch = (ld16 + 31) / 32;
-    const int grid = k1_parts(sm_count);
+    // one CTA per SM, but never more CTAs than there are row groups for their warps: a 1000-row collection runs on 16
+    // CTAs, whose lists the last one merges in a fraction of the time 148 would take (18.6 us -> see profiles/)
+    const int64_t n_groups = mask ? (n_rows + 63) / 64 : (n_rows + K1_R - 1) / K1_R;
+    const int grid = (int)std::min<int64_t>(k1_parts(sm_count), std::max<int64_t>(1, (n_groups + K1_WARPS - 1) / K1_WARPS));
+    if (parts_out) *parts_out = grid;
     // fuse the final merge when every per-CTA list fits the in-kernel selection's staging area
     const int fuse_stage = (grid * k <= 8192) ? grid * k : 0;
     if (fused) *fused = fuse_stage > 0;

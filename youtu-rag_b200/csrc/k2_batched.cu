@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "../../include/yrb200.h"
@@ -434,9 +435,11 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
     // threshold kernel, main launch — kept for A/B runs)
     static int fuse_env = -1;
     if (fuse_env < 0) fuse_env = getenv("YRB_K2_FUSE") ? atoi(getenv("YRB_K2_FUSE")) : 1;
+    static bool fuse_ok[2] = {true, true};  // [0] one-CTA kernel, [1] pair kernel: cleared if a cooperative launch is refused
     unsigned int* sync_ctr = reinterpret_cast<unsigned int*>(s->cand_cnt + (size_t)s->slots * k2::MAX_Q);  // zeroed with the counts
     for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
-        const bool fuse = fuse_env != 0;
+        const bool use_pair_now = (nq - c0 > k2::BLOCK_Q) && !rowmap && k2_use_pair(force_pair);
+        const bool fuse = fuse_env != 0 && fuse_ok[use_pair_now ? 1 : 0];
         const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
         const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
@@ -484,8 +487,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
                                                  s->cand_cnt, fz ? s->tops : nullptr, fz ? m_tops2 : 0, qn, xn, fz ? s->thr0 : nullptr,
                                                  fz ? sync_ctr : nullptr, st);
                 if (e != cudaSuccess && fz) {  // cooperative launch refused: redo this chunk with the separate sampling pass
+                    fprintf(stderr, "yrb200: cooperative launch of k2_gemm_topk_pair refused (%s); sampling runs as separate launches\n",
+                            cudaGetErrorString(e));
                     cudaGetLastError();
-                    fuse_env = 0;
+                    fuse_ok[1] = false;
                     c0 -= k2::MAX_Q;
                     continue;
                 }
@@ -529,8 +534,10 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         {
             cudaError_t e = gemm(iters, thr, fz ? s->tops : nullptr, fz ? m_tops : 0, fz ? s->thr0 : nullptr, fz ? sync_ctr : nullptr);
             if (e != cudaSuccess && fz) {  // cooperative launch refused: redo this chunk with the separate sampling pass
+                fprintf(stderr, "yrb200: cooperative launch of k2_gemm_topk refused (%s); sampling runs as separate launches\n",
+                        cudaGetErrorString(e));
                 cudaGetLastError();
-                fuse_env = 0;
+                fuse_ok[0] = false;
                 c0 -= k2::MAX_Q;
                 continue;
             }

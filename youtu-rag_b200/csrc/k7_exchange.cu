@@ -14,6 +14,7 @@
 // Payload is KiB-scale (C5: 80 KiB per rank): latency-bound, a few microseconds.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -60,58 +61,67 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+// A bounded grid walks the queries (CTA c takes q = c, c + grid, …): every rank visits the queries in the same
+// order, so the lowest unfinished query of every rank is always held by a resident CTA and the flag waits cannot
+// depend on how many CTAs the scheduler keeps resident beside a running scan.
+constexpr int EX_MAX_GRID = 64;
+constexpr long long EX_TIMEOUT_CLK = 120000000000ll;  // ~60 s: a peer that is this late is gone; trap instead of hanging
+
 __global__ void __launch_bounds__(EX_THREADS) exchange_merge_kernel(ExArgs a) {
     __shared__ GKeyX sk[EX_CAP];
     __shared__ int cnt;
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int par = a.epoch & 1u;
-    const size_t slot_q = ((size_t)par * a.world + a.rank) * a.nq_cap + q;  // where MY keys land in every buffer
-    // 1. push this query's keys into every rank's buffer (own copy included)
-    for (int i = tid; i < a.world * a.k; i += EX_THREADS) {
-        const int p = i / a.k, j = i - p * a.k;
-        a.slots[p][slot_q * a.k_cap + j] = a.local_keys[(size_t)q * a.k + j];
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. raise my flag on every rank, then wait for every rank's flag here
-    if (tid < a.world) st_release_sys(a.flags[tid] + slot_q, a.epoch);
-    if (tid < a.world) {
-        const uint32_t* f = a.flags[a.rank] + ((size_t)par * a.world + tid) * a.nq_cap + q;
-        const long long t0 = clock64();
-        while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
-            if (clock64() - t0 > 8000000000ll) __trap();  // a peer never arrived: fail instead of hanging the GPU
-        }
-    }
-    __syncthreads();
-    // 3. merge world * k candidates by (score desc, global id asc)
-    const int n = a.world * a.k;
-    const int npow = next_pow2(n);
-    if (tid == 0) cnt = 0;
-    const uint64_t* mine = a.slots[a.rank];
-    for (int i = tid; i < npow; i += EX_THREADS) {
-        GKeyX g{0u, 0u, 0};
-        if (i < n) {
+    for (int q = blockIdx.x; q < a.nq; q += gridDim.x) {
+        const size_t slot_q = ((size_t)par * a.world + a.rank) * a.nq_cap + q;  // where MY keys land in every buffer
+        // 1. push this query's keys into every rank's buffer (own copy included)
+        for (int i = tid; i < a.world * a.k; i += EX_THREADS) {
             const int p = i / a.k, j = i - p * a.k;
-            const uint64_t key = __ldcg(mine + (((size_t)par * a.world + p) * a.nq_cap + q) * a.k_cap + j);
-            if (key != 0ull) {
-                g.sbits = (uint32_t)(key >> 32);
-                g.valid = 1u;
-                g.gid = a.row_base[p] + (int64_t)key_row(key);
+            a.slots[p][slot_q * a.k_cap + j] = a.local_keys[(size_t)q * a.k + j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        // 2. raise my flag on every rank, then wait for every rank's flag here
+        if (tid < a.world) st_release_sys(a.flags[tid] + slot_q, a.epoch);
+        if (tid < a.world) {
+            const uint32_t* f = a.flags[a.rank] + ((size_t)par * a.world + tid) * a.nq_cap + q;
+            const long long t0 = clock64();
+            while ((int32_t)(ld_acquire_sys(f) - a.epoch) < 0) {
+                if (clock64() - t0 > EX_TIMEOUT_CLK) __trap();
             }
         }
-        sk[i] = g;
+        __syncthreads();
+        // 3. merge world * k candidates by (score desc, global id asc)
+        const int n = a.world * a.k;
+        const int npow = next_pow2(n);
+        if (tid == 0) cnt = 0;
+        const uint64_t* mine = a.slots[a.rank];
+        for (int i = tid; i < npow; i += EX_THREADS) {
+            GKeyX g{0u, 0u, 0};
+            if (i < n) {
+                const int p = i / a.k, j = i - p * a.k;
+                const uint64_t key = __ldcg(mine + (((size_t)par * a.world + p) * a.nq_cap + q) * a.k_cap + j);
+                if (key != 0ull) {
+                    g.sbits = (uint32_t)(key >> 32);
+                    g.valid = 1u;
+                    g.gid = a.row_base[p] + (int64_t)key_row(key);
+                }
+            }
+            sk[i] = g;
+        }
+        block_bitonic_desc(sk, npow, BetterGX());
+        int local = 0;
+        for (int i = tid; i < a.k; i += EX_THREADS) {
+            const bool ok = (i < n) && sk[i].valid;
+            a.ids[(size_t)q * a.k + i] = ok ? sk[i].gid : -1;
+            a.scores[(size_t)q * a.k + i] = ok ? bits_score(sk[i].sbits) : -INFINITY;
+            local += ok;
+        }
+        if (local) atomicAdd(&cnt, local);
+        __syncthreads();
+        if (tid == 0 && a.counts) a.counts[q] = cnt;
+        __syncthreads();  // sk / cnt are reused by the next query
     }
-    block_bitonic_desc(sk, npow, BetterGX());
-    int local = 0;
-    for (int i = tid; i < a.k; i += EX_THREADS) {
-        const bool ok = (i < n) && sk[i].valid;
-        a.ids[(size_t)q * a.k + i] = ok ? sk[i].gid : -1;
-        a.scores[(size_t)q * a.k + i] = ok ? bits_score(sk[i].sbits) : -INFINITY;
-        local += ok;
-    }
-    if (local) atomicAdd(&cnt, local);
-    __syncthreads();
-    if (tid == 0 && a.counts) a.counts[q] = cnt;
 }
 
 }  // namespace yrb
@@ -219,7 +229,7 @@ int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq,
     a.ids = dev_out_ids;
     a.scores = dev_out_scores;
     a.counts = dev_out_counts;
-    yrb::exchange_merge_kernel<<<nq, yrb::EX_THREADS, 0, (cudaStream_t)stream>>>(a);
+    yrb::exchange_merge_kernel<<<std::min(nq, yrb::EX_MAX_GRID), yrb::EX_THREADS, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return xfail(YRB_ERR_CUDA, std::string("exchange_merge_kernel: ") + cudaGetErrorString(e));
     return YRB_OK;
@@ -232,6 +242,7 @@ int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq,
 int yrb_exchange_search(yrb_exchange* ex, yrb_index* ix, const float* queries, int nq, int k, const uint32_t* dev_mask,
                         const int64_t* dev_row_base, int64_t* out_ids, float* out_scores, int32_t* out_counts) {
     using namespace yrbi;
+    Nvtx nvtx_("yrb_exchange_search");
     if (!ex || !ix || !queries || !dev_row_base || !out_ids || !out_scores) return fail(YRB_ERR_INVALID, "NULL argument");
     if (nq < 1 || nq > ex->nq_cap || k < 1 || k > ex->k_cap) return fail(YRB_ERR_INVALID, "nq / k exceed the exchange's capacity");
     if (ix->device != ex->device) return fail(YRB_ERR_INVALID, "index and exchange live on different devices");

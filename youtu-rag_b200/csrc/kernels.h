@@ -43,7 +43,8 @@ struct K1Out {
 };
 cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
-                      unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st);
+                      unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st,
+                      int* parts_out = nullptr);  // CTAs launched = per-CTA lists written (<= k1_parts(sm_count))
 
 // K1Q: up to 4 prepared fp32 queries ([nq][ld] fp32 + squared norms, from launch_ingest) against fp32 rows in one
 // pass; one shared mask; k <= 32.  Writes per-CTA sorted lists part_keys[q][cta][k]; finish with

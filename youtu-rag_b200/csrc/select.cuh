@@ -163,13 +163,14 @@ __device__ __forceinline__ void select_topk_block(const SelectArgs& a, const int
         // ---- fallback: chunked bitonic merging straight from the segments (slow, exact)
         int have = 0;
         int seg = 0;
+        const int stage2 = 1 << (31 - __clz(stage));  // the bitonic passes below pad to a power of two: stay inside the stage
         while (seg < a.n_seg) {
             __syncthreads();
             if (tid == 0) s_n = have;
             __syncthreads();
             int seg_end = seg;
             int budget = have;
-            while (seg_end < a.n_seg && budget + seg_count(a, seg_end, q) <= stage) {
+            while (seg_end < a.n_seg && budget + seg_count(a, seg_end, q) <= stage2) {
                 budget += seg_count(a, seg_end, q);
                 ++seg_end;
             }

@@ -111,6 +111,7 @@ int for_pieces(const yrb_sharded* sh, int64_t g0, int64_t n, Fn fn) {
 
 // ------------------------------------------------------------------ one shard's part of a search (worker thread)
 int shard_search(yrb_sharded* sh, int s) {
+    Nvtx nvtx_("yrb_sharded_search/shard");
     const SearchJob& j = sh->job;
     yrb_index* ix = sh->shard[s];
     if (!((j.active_mask >> s) & 1u)) return YRB_OK;
@@ -251,6 +252,7 @@ int sharded_search(yrb_sharded* sh, const float* queries, int nq, int k, const y
     if (nq < 1 || !queries) return fail(YRB_ERR_INVALID, "need at least one query");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
     if (!out_ids || !out_scores) return fail(YRB_ERR_INVALID, "output buffers are NULL");
+    Nvtx nvtx_("yrb_sharded_search");
     std::lock_guard<std::mutex> g(sh->mu);
     int64_t live = 0;
     for (int s = 0; s < sh->n; ++s) live += sh->shard[s]->rows - sh->shard[s]->n_dead;
@@ -492,7 +494,9 @@ int yrb_sharded_append_device_f32(yrb_sharded* sh, const float* dev_rows, int64_
             CK(cudaMalloc(&sh->d_peer_stage[s], need * 4));
             sh->peer_stage_floats[s] = need;
         }
-        CK(cudaMemcpyPeer(sh->d_peer_stage[s], sh->devices[s], src, src_device, need * 4));
+        // on the shard's own stream: the ingest kernel that follows is ordered behind the copy (a plain
+        // cudaMemcpyPeer runs on the legacy stream, which a non-blocking stream does not wait for)
+        CK(cudaMemcpyPeerAsync(sh->d_peer_stage[s], sh->devices[s], src, src_device, need * 4, ix->stream));
         return yrb_index_append_device_f32(ix, sh->d_peer_stage[s], cnt, nullptr);
     });
     if (rc) {

@@ -178,7 +178,7 @@ class Index:
                 _lib.yrb_index_destroy(self._h)
             except Exception:  # noqa: BLE001 - interpreter shutdown: module globals may already be gone
                 pass
-            self._h = C.c_void_p()
+            self._h = None
 
     __del__ = close
 
@@ -341,7 +341,7 @@ class ShardedIndex(Index):
                 _lib.yrb_sharded_destroy(self._h)
             except Exception:  # noqa: BLE001
                 pass
-            self._h = C.c_void_p()
+            self._h = None
 
     __del__ = close
 
@@ -525,7 +525,7 @@ class Exchange:
                 _lib.yrb_exchange_destroy(self._h)
             except Exception:  # noqa: BLE001
                 pass
-            self._h = C.c_void_p()
+            self._h = None
 
     __del__ = close
 
