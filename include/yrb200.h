@@ -148,6 +148,20 @@ YRB_API int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k,
                      const uint32_t* mask, int64_t* out_ids, float* out_scores,
                      int32_t* out_counts);
 
+/* Search with options.  `min_score`: the retriever's similarity threshold (base_retriever.py:71 keeps a hit when
+ * `score >= threshold`) applied INSIDE the scan — it is the initial bound of every running top-k list (K1) and of the
+ * epilogue's survivor test (K2), so rows below it are never candidates and out_counts counts qualifying hits only.
+ * The result equals filtering the plain top-k on the host (the list is sorted; the threshold only cuts its tail).
+ * -INFINITY (or opts == NULL) = no threshold.  `w` (shared) or `wheres` (one per query) or neither; `mask` as in
+ * yrb_index_search (not with `wheres`). */
+typedef struct yrb_search_opts {
+    float min_score;
+    int32_t reserved[7]; /* zero */
+} yrb_search_opts;
+YRB_API int yrb_index_search_ex(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w,
+                                const yrb_where* const* wheres, const uint32_t* mask, const yrb_search_opts* opts,
+                                int64_t* out_ids, float* out_scores, int32_t* out_counts);
+
 /* One filter per query (wheres[q] may be NULL = no filter): the batched form of the reference's
  * per-column searches (utu/tools/text2sql/unified_schemalink_valuelink.py:289-303 loops
  * CourseSearcher.search, chroma_retrical_text2sql.py:148-194, one filtered search per column with
@@ -158,7 +172,9 @@ YRB_API int yrb_index_search_multi(yrb_index* ix, const float* queries, int nq, 
 
 /* All-device variant for resident inputs (bench `value`, sharded search): queries fp32 [nq, dim]
  * on the device, mask device words or NULL, outputs = nq*k packed 64-bit selection keys
- * (see yrb_key_*), best first, 0 = empty slot.  Asynchronous on `stream`.
+ * (see yrb_key_*), best first, 0 = empty slot.  Asynchronous on `stream` — with one exception: a batch (nq >= 2)
+ * under a shared mask over >= 65536 rows first counts the passing rows (K8 decides on the host whether to gather them),
+ * which synchronises `stream` once.
  * All searches of one index share its scratch (per-CTA lists, ticket counters, candidate buffers):
  * enqueue them on ONE stream, or order streams with events; concurrent searches need separate indexes. */
 YRB_API int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int k,
@@ -234,6 +250,9 @@ YRB_API int yrb_sharded_search(yrb_sharded* sh, const float* queries, int nq, in
                                const uint32_t* mask, int64_t* out_ids, float* out_scores, int32_t* out_counts);
 YRB_API int yrb_sharded_search_multi(yrb_sharded* sh, const float* queries, int nq, int k, const yrb_where* const* wheres,
                                      int64_t* out_ids, float* out_scores, int32_t* out_counts);
+YRB_API int yrb_sharded_search_ex(yrb_sharded* sh, const float* queries, int nq, int k, const yrb_where* w,
+                                  const yrb_where* const* wheres, const uint32_t* mask, const yrb_search_opts* opts,
+                                  int64_t* out_ids, float* out_scores, int32_t* out_counts);
 YRB_API int yrb_sharded_stats(const yrb_sharded* sh, int64_t* out_kernel_launches, int64_t* out_searches);
 
 /* Force a kernel family for tests/bench: 0 auto, 1 K1 (GEMV + in-register top-k),
@@ -247,6 +266,10 @@ YRB_API int yrb_index_set_reserved_sms(yrb_index* ix, int n);
 /* launches issued by this index since creation (bench `gpu_launches`), and the duration in ms of
  * the dominant kernel of the last search measured with CUDA events when enabled. */
 YRB_API int yrb_index_stats(const yrb_index* ix, int64_t* out_kernel_launches);
+/* Filter caches: a `where` program evaluated over unchanged rows / tombstones / columns reuses its bitmask (K4 skipped)
+ * and, for batches, the gathered rows of a selective filter (K8 skipped: agents repeat the same knowledge-base filter,
+ * kb_search_toolkit.py:63-96).  Any append, delete or metadata write invalidates both.  Counters since creation. */
+YRB_API int yrb_index_cache_stats(const yrb_index* ix, int64_t* out_filter_hits, int64_t* out_compaction_hits);
 /* CUDA-event timing of the dominant kernel (K1 scan / K2 GEMM) of every search issued while
  * enabled: events are recorded on the launching stream around that kernel only.  read() waits for
  * the recorded events, returns the summed duration and launch count since the last read, resets. */

@@ -143,7 +143,7 @@ class FakeIndex:
         return ox.pack_mask(m), int(m.sum())
 
     # ------------------------------------------------------------ search
-    def search(self, queries: np.ndarray, k: int, where=None, mask=None, wheres=None):
+    def search(self, queries: np.ndarray, k: int, where=None, mask=None, wheres=None, min_score=None):
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -158,6 +158,9 @@ class FakeIndex:
         for j in range(nq):
             m = self._mask(wheres[j] if wheres is not None else where, mask)
             qi, si = ox.exact_topk(self._rows, ox.prepare(q[j], self.metric, self.dtype)[0], k, self.metric, m)
+            if min_score is not None:
+                keep = si.astype(np.float32) >= np.float32(min_score)
+                qi, si = qi[keep], si[keep]
             counts[j] = qi.shape[0]
             ids[j, :qi.shape[0]], scores[j, :qi.shape[0]] = qi, si
         return ids, scores, counts

@@ -194,3 +194,69 @@ def test_k6_large_k_any_path(dtype):
     small = build(unit_rows(50, d, 24), "cosine", dtype)
     ids, _, counts = small.search(q, 4097)       # clamped to the collection size
     assert int(counts[0]) == 50 and (ids[0, 50:] == -1).all()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_score_threshold_inside_the_scan_equals_filtering_the_result(metric, dtype):
+    """f4 (base_retriever.py:71: keep a hit when score >= threshold): `min_score` is the initial bound of the running
+    top-k lists / the epilogue's survivor test on every kernel family — K1 (k <= 32 and k = 100), K2 or K1Q (batches),
+    K6 (k > 128), with a bitmask, and over a collection sharded inside the process — and returns exactly the hits a
+    host-side filter of the plain result keeps, a hit whose score EQUALS the threshold included."""
+    n, d = 30_000, 256
+    x = unit_rows(n, d, 31)
+    q = unit_rows(6, d, 32)
+    m = np.random.default_rng(3).random(n) < 0.3
+    ix = build(x, metric, dtype)
+    sh = native.ShardedIndex(d, metric, dtype, [0, 0, 0], block_rows=1024)
+    sh.append(x)
+    for index in (ix, sh):
+        for queries, k, kw in ((q[:1], 10, {}), (q[:1], 100, {}), (q, 10, {}), (q, 100, {}), (q[:1], 200, {}),
+                               (q[:1], 10, {"mask": ox.pack_mask(m)}), (q, 10, {"mask": ox.pack_mask(m)})):
+            ids, scores, counts = index.search(queries, k, **kw)
+            for pos in (0, 4, k - 1):
+                t = float(scores[0, pos])                                    # exactly a returned score: must be kept
+                for thr in (t, float(np.nextafter(np.float32(t), np.float32(np.inf)))):
+                    i2, s2, c2 = index.search(queries, k, min_score=thr, **kw)
+                    for j in range(queries.shape[0]):
+                        keep = scores[j, :counts[j]] >= np.float32(thr)
+                        assert c2[j] == keep.sum(), (k, pos, j, c2[j], keep.sum())
+                        np.testing.assert_array_equal(i2[j, :c2[j]], ids[j, :counts[j]][keep])
+                        np.testing.assert_array_equal(s2[j, :c2[j]].view(np.uint32), scores[j, :counts[j]][keep].view(np.uint32))
+                        assert (i2[j, c2[j]:] == -1).all()
+    ids, scores, counts = ix.search(q, 10, min_score=1e9)                    # nothing qualifies
+    assert (counts == 0).all() and (ids == -1).all()
+    sh.close()
+
+
+def test_retriever_threshold_runs_inside_the_store():
+    """VectorRetriever hands its similarity threshold to a store that supports it; results equal the host-side rule."""
+    import asyncio
+
+    from youtu_rag_b200 import B200VectorStore, Chunk, RetrieverConfig, VectorRetriever, VectorStoreConfig
+    from youtu_rag_b200.base import BaseEmbedder
+
+    n, d = 5000, 64
+    x = unit_rows(n, d, 41)
+    qs = unit_rows(3, d, 42)
+
+    class Emb(BaseEmbedder):
+        async def embed_texts(self, texts):
+            return [qs[int(t)].tolist() for t in texts]
+
+        async def embed_query(self, query):
+            return qs[int(query)].tolist()
+
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_thr", index_params={"storage_dtype": "f32"}))
+    asyncio.run(s.add_chunks([Chunk(id=f"c{i}", document_id="d", content="", chunk_index=i, metadata={}, embedding=x[i].tolist()) for i in range(n)]))
+    plain = asyncio.run(s.search(qs[0].tolist(), 20))
+    thr = (plain[7][1] + plain[8][1]) / 2                                     # a Python double between two scores
+    r = VectorRetriever(s, Emb(), RetrieverConfig(top_k=20, similarity_threshold=min(1.0, max(0.0, thr))))
+    got = asyncio.run(r.retrieve("0"))
+    assert [(g.chunk.id, g.rank) for g in got] == [(c.id, i + 1) for i, (c, sc) in enumerate(plain) if sc >= thr]
+    batch = asyncio.run(r.batch_retrieve(["0", "1", "2"]))
+    assert [(g.chunk.id, g.score) for g in batch[0]] == [(g.chunk.id, g.score) for g in got]
+    for j in (1, 2):
+        want = [(c.id, sc) for c, sc in asyncio.run(s.search(qs[j].tolist(), 20)) if sc >= thr]
+        assert [(g.chunk.id, g.score) for g in batch[j]] == want
+    s.close()

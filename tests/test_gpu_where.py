@@ -127,3 +127,38 @@ def test_where_from_reference_filter_producers():
         assert c == min(5, int(want.sum()))
         if c:
             check_topk(ids[0, :c], scores[0, :c], rows, qp, 5, "cosine", "bf16", mask=want)
+
+
+def test_repeated_filters_hit_the_caches_and_mutations_invalidate_them():
+    """the same `where` over unchanged rows reuses its bitmask (K4) and, for a batch under a
+    selective filter, the gathered rows (K8) — and any append / delete / metadata write drops both."""
+    import asyncio
+
+    from tests.helpers import unit_rows
+    from youtu_rag_b200 import B200VectorStore, Chunk, VectorStoreConfig
+
+    n, d = 70_000, 64                                   # >= 65536 rows: K8 territory
+    x = unit_rows(n, d, 4)
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_cache", index_params={"storage_dtype": "bf16"}))
+    asyncio.run(s.add_chunks([Chunk(id=f"c{i}", document_id=f"d{i % 10}", content="", chunk_index=i, metadata={"kb": i % 10}, embedding=x[i].tolist())
+                              for i in range(n)]))
+    q = unit_rows(4, d, 5)
+    f = {"kb": 3}
+
+    def ids(res):
+        return [[c.id for c, _ in r] for r in res]
+
+    first = asyncio.run(s.search_batch(q, top_k=5, filters=f))
+    h0 = s.index.cache_stats()
+    again = asyncio.run(s.search_batch(q, top_k=5, filters=f))
+    h1 = s.index.cache_stats()
+    assert ids(again) == ids(first) and h1[0] == h0[0] + 1 and h1[1] == h0[1] + 1          # both caches hit
+    single = asyncio.run(s.search(q[0].tolist(), 5, f))
+    assert [c.id for c, _ in single] == ids(first)[0] and s.index.cache_stats()[0] == h1[0] + 1
+    victim = ids(first)[0][0]
+    asyncio.run(s.delete([victim]))                                                          # tombstone → new epoch
+    after = asyncio.run(s.search_batch(q, top_k=5, filters=f))
+    assert s.index.cache_stats() == (h1[0] + 1, h1[1]) and victim not in ids(after)[0] and ids(after)[0][:4] == ids(first)[0][1:]
+    asyncio.run(s.add_chunks([Chunk(id="new", document_id="d3", content="", chunk_index=0, metadata={"kb": 3}, embedding=q[1].tolist())]))
+    assert ids(asyncio.run(s.search_batch(q, top_k=5, filters=f)))[1][0] == "new"            # the append is seen
+    s.close()

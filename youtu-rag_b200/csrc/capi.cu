@@ -33,6 +33,19 @@ int fail(int code, const char* fmt, ...) {
 const std::string& last_error() { return g_err; }
 void set_error(const std::string& m) { g_err = m; }
 
+}  // namespace yrbi
+namespace yrb {
+uint64_t score_floor_key(float min_score) {
+    if (!(min_score > -INFINITY)) return 0ull;   // -inf or NaN: no threshold
+    // monotone bit pattern of the largest float below min_score, all row bits set: key > floor  <=>  score >= min_score
+    const float lo = nextafterf(min_score, -INFINITY);
+    uint32_t u;
+    memcpy(&u, &lo, 4);
+    const uint32_t m = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((uint64_t)m << 32) | 0xffffffffull;
+}
+}  // namespace yrb
+namespace yrbi {
 int col_width(int t) { return t == YRB_COL_I64 || t == YRB_COL_F64 ? 8 : (t == YRB_COL_CODE ? 4 : 1); }
 
 DevicePool* device_pool(int device) {
@@ -90,6 +103,7 @@ int ensure_capacity(yrb_index* ix, int64_t want) {
     const size_t ow = (size_t)mask_words(ix->capacity) * 4, nw = (size_t)mask_words(cap) * 4;
     if ((rc = regrow(&ix->d_live, ix->capacity ? ow : 0, nw, true, ix->stream))) return rc;
     if ((rc = regrow(&ix->d_mask, 0, nw, true, ix->stream))) return rc;
+    ix->dmask_key = 0;   // the cached filter mask lived in the old buffer
     if ((rc = regrow(&ix->d_usermask, 0, nw, true, ix->stream))) return rc;
     ix->h_live.resize(mask_words(cap), 0u);
     for (auto& kv : ix->cols) {
@@ -245,23 +259,49 @@ int build_prog(yrb_index* ix, const yrb_where* w) {
     return YRB_OK;
 }
 
+static uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+
 // evaluates w (and/or ANDs a device mask) into ix->d_mask; returns the mask pointer to scan with
 int resolve_mask(yrb_index* ix, const yrb_where* w, const uint32_t* dev_extra, const uint32_t** out, cudaStream_t st,
                  bool count) {
     Nvtx nvtx_("k4_filter");
     const uint32_t* live = ix->n_dead > 0 ? ix->d_live : nullptr;
+    ix->cur_mask_key = 0;
     if (w) {
         int rc = build_prog(ix, w);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(ix->d_prog, ix->h_prog, sizeof(yrb::WhereProgDev), cudaMemcpyHostToDevice, st));
-        if (count) CK(cudaMemsetAsync(ix->d_pass, 0, 8, st));
-        CK(yrb::launch_where(ix->d_prog, ix->rows, live, dev_extra, ix->d_mask, count ? ix->d_pass : nullptr, st));
-        ix->launches++;
+        // the same program over unchanged rows, tombstones and columns selects the same rows: reuse the mask
+        uint64_t key = 0;
+        if (!dev_extra && !count) {
+            const yrb::WhereProgDev* p = ix->h_prog;
+            key = fnv1a(&p->n_leaves, sizeof p->n_leaves);
+            key = fnv1a(&p->n_postfix, sizeof p->n_postfix, key);
+            key = fnv1a(p->leaves, sizeof(yrb::WhereLeafDev) * (size_t)p->n_leaves, key);
+            key = fnv1a(p->operands, sizeof(int64_t) * (size_t)w->n_operands, key);
+            key = fnv1a(p->postfix, sizeof(int32_t) * (size_t)p->n_postfix, key);
+            key = fnv1a(&ix->epoch, sizeof ix->epoch, key);
+            key |= 1ull;
+        }
+        if (key && key == ix->dmask_key) {
+            ix->cache_hits_k4++;
+        } else {
+            CK(cudaMemcpyAsync(ix->d_prog, ix->h_prog, sizeof(yrb::WhereProgDev), cudaMemcpyHostToDevice, st));
+            if (count) CK(cudaMemsetAsync(ix->d_pass, 0, 8, st));
+            CK(yrb::launch_where(ix->d_prog, ix->rows, live, dev_extra, ix->d_mask, count ? ix->d_pass : nullptr, st));
+            ix->launches++;
+            ix->dmask_key = key;
+        }
+        ix->cur_mask_key = key;
         *out = ix->d_mask;
     } else if (dev_extra) {
         if (live) {
             CK(yrb::launch_mask_and(dev_extra, live, mask_words(ix->rows), ix->d_mask, st));
             ix->launches++;
+            ix->dmask_key = 0;
             *out = ix->d_mask;
         } else {
             *out = dev_extra;
@@ -371,8 +411,10 @@ int prof_mark(yrb_index* ix, cudaStream_t st) {
 // raw fp32 queries [nq, dim] on the device → nq*k keys (and, when `decode`, ix->d_ids/d_scores/d_counts).
 // K1 prepares the query in its own prologue; K2 needs the prepared bf16 matrix (K5 launch).
 int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, int64_t mask_q_stride,
-                uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st, const yrb::XShard* xs) {
+                uint64_t* out_keys, int64_t* ids, float* scores, int32_t* counts, cudaStream_t st, const yrb::XShard* xs,
+                float min_score) {
     Nvtx nvtx_("scan_select");
+    const uint64_t floor_key = yrb::score_floor_key(min_score);
     if (xs) ids = nullptr, scores = nullptr, counts = nullptr;  // the cross-shard merge writes the results
     const bool decode = ids != nullptr;
     const int sms = std::max(2, ix->sm_count - ix->reserved_sms) & ~1;  // even: K2 runs CTA clusters of 2
@@ -398,7 +440,18 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         const float* k2_sqnorm = ix->d_sqnorm;
         int64_t k2_n = ix->rows;
         bool compacted = false, use_rowmap = false;
-        if (mask && mask_q_stride == 0 && ix->rows >= 65536) {
+        const uint64_t mkey = ix->cur_mask_key;
+        if (mask && mask_q_stride == 0 && ix->rows >= 65536 && mkey && mkey == ix->cp_key && ix->cp_pass >= k) {
+            // this filter's rows were gathered by an earlier search and nothing changed since: no count, no
+            // synchronisation, no gather
+            ix->cache_hits_k8++;
+            use_rowmap = ix->cp_rowmap;
+            if (!use_rowmap) k2_rows = ix->d_cp_rows;
+            k2_sqnorm = ix->d_cp_sqnorm;
+            k2_n = ix->cp_pass;
+            mask = nullptr;
+            compacted = true;
+        } else if (mask && mask_q_stride == 0 && ix->rows >= 65536) {
             const size_t nb = yrb::compact_scratch_words(ix->rows);
             if (nb > ix->cp_blocks_cap) {
                 CK(cudaStreamSynchronize(st));
@@ -407,6 +460,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
                 ix->cp_blocks_cap = nb;
             }
             if (!ix->h_pass) CK(cudaMallocHost(&ix->h_pass, 8));
+            ix->cp_key = 0;
             CK(yrb::launch_compact_count(mask, ix->rows, ix->d_cp_blocks, ix->d_pass, st));
             CK(cudaMemcpyAsync(ix->h_pass, ix->d_pass, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -443,6 +497,9 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
                 k2_n = pass;
                 mask = nullptr;
                 compacted = true;
+                ix->cp_key = mkey;     // 0 (no key: a caller-supplied mask) is never matched
+                ix->cp_pass = pass;
+                ix->cp_rowmap = use_rowmap;
             }
         }
         CK(yrb::launch_ingest(dev_q, nq, ix->dim, ix->ld, ix->metric, ix->dtype, ix->d_q, ix->d_qsq, st));
@@ -459,7 +516,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         rc = yrb::k2_search(ix->k2, k2_rows, k2_n, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
                             mask_q_stride, ix->metric, ix->d_qsq, k2_sqnorm, out_keys, ids, scores, counts, sms, st,
                             &launches, err, ea, eb, pair, (compacted && use_rowmap) ? ix->d_cp_map : nullptr, ix->rows,
-                            compacted ? nullptr : xs);
+                            compacted ? nullptr : xs, min_score);
         if (rc) set_error(err);
         ix->launches += launches;
         if (!rc && compacted) {
@@ -480,7 +537,8 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         for (int c0 = 0; c0 < nq; c0 += yrb::K1Q_MAX_Q) {
             const int n = std::min(yrb::K1Q_MAX_Q, nq - c0);
             CK(yrb::launch_k1q_f32(ix->d_rows, ix->rows, ix->ld, reinterpret_cast<const float*>(ix->d_q) + (size_t)c0 * ix->ld, n,
-                                   ix->d_qsq + c0, ix->d_sqnorm, ix->metric, mask, k, ix->d_parts + (size_t)c0 * parts * k, sms, st));
+                                   ix->d_qsq + c0, ix->d_sqnorm, ix->metric, mask, k, ix->d_parts + (size_t)c0 * parts * k, sms, st,
+                                   floor_key));
             ix->launches++;
         }
         // one selection launch for the whole batch: query q's per-CTA lists sit at d_parts[q][cta][k]
@@ -495,6 +553,7 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
             uint64_t* pk = ix->d_parts + (size_t)j * parts * k;
             yrb::K1Out o{out_keys + (size_t)j * k, ids ? ids + (size_t)j * k : nullptr,
                          scores ? scores + (size_t)j * k : nullptr, counts ? counts + j : nullptr};
+            o.floor_key = floor_key;
             yrb::XShard xj{};
             if (xs) {
                 xj = *xs;
@@ -572,7 +631,8 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
     }
     for (int j = 0; j < nq; ++j) {
         CK(yrb::launch_scores(ix->d_rows, ix->dtype, ix->rows, ix->dim, ix->ld, dev_q + (size_t)j * ix->dim, ix->d_sqnorm,
-                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, ix->d_rowkeys, ix->sm_count, st));
+                              ix->metric, mask ? mask + (size_t)j * mask_q_stride : nullptr, ix->d_rowkeys, ix->sm_count, st,
+                              floor_key));
         CK(yrb::launch_select(ix->d_rowkeys, ix->rows, k, out_keys + (size_t)j * k, ix->d_select, ix->sm_count, st));
         ix->launches += 15;
     }
@@ -627,6 +687,7 @@ int append_device_locked(yrb_index* ix, const float* dev_rows, int64_t n, cudaSt
     rc = mark_appended(ix, ix->rows, n);
     if (rc) return rc;
     ix->rows += n;
+    ix->epoch++;
     return YRB_OK;
 }
 
@@ -888,6 +949,7 @@ int yrb_index_append_raw(yrb_index* ix, const void* rows, const float* sqnorm, i
     CK(cudaStreamSynchronize(ix->stream));
     if ((rc = mark_appended(ix, ix->rows, n))) return rc;
     ix->rows += n;
+    ix->epoch++;
     return YRB_OK;
 }
 
@@ -916,6 +978,7 @@ int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int liv
         wmin = std::min(wmin, w);
         wmax = std::max(wmax, w);
     }
+    ix->epoch++;
     return upload_words(ix->d_live, ix->h_live, wmin, wmax + 1, ix->stream);
 }
 
@@ -943,6 +1006,7 @@ int yrb_index_truncate(yrb_index* ix, int64_t rows) {
         if ((rc = upload_words(kv.second.present, kv.second.present_host, w0, w1, ix->stream))) return rc;
     }
     ix->rows = rows;
+    ix->epoch++;
     return YRB_OK;
 }
 
@@ -953,6 +1017,7 @@ int yrb_index_clear(yrb_index* ix) {
     if (rc) return rc;
     CK(cudaStreamSynchronize(ix->stream));
     ix->rows = 0;
+    ix->epoch++;
     ix->n_dead = 0;
     std::fill(ix->h_live.begin(), ix->h_live.end(), 0u);
     CK(cudaMemsetAsync(ix->d_live, 0, (size_t)mask_words(ix->capacity) * 4, ix->stream));
@@ -987,6 +1052,7 @@ int yrb_index_column_write(yrb_index* ix, int col, int col_type, int64_t row_beg
         if (present[i]) c.present_host[r >> 5] |= (1u << (r & 31));
         else c.present_host[r >> 5] &= ~(1u << (r & 31));
     }
+    ix->epoch++;
     return upload_words(c.present, c.present_host, row_begin >> 5, ((row_begin + n - 1) >> 5) + 1, ix->stream);
 }
 
@@ -1014,7 +1080,7 @@ int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64
 
 static int search_host(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w,
                        const yrb_where* const* per_query, const uint32_t* mask, int64_t* out_ids, float* out_scores,
-                       int32_t* out_counts) {
+                       int32_t* out_counts, float min_score = -INFINITY) {
     Nvtx nvtx_("yrb_index_search");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (nq < 1 || !queries) return fail(YRB_ERR_INVALID, "need at least one query");
@@ -1056,7 +1122,7 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     } else {
         rc = resolve_mask(ix, w, dev_extra, &m, st, false);
     }
-    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, m_stride, ix->d_keys, ix->d_ids, ix->d_scores, ix->d_counts, st);
+    if (!rc) rc = scan_select(ix, ix->d_qf32, nq, ke, m, m_stride, ix->d_keys, ix->d_ids, ix->d_scores, ix->d_counts, st, nullptr, min_score);
     if (!rc) {
         cudaError_t e = zero_copy ? cudaSuccess : cudaMemcpyAsync(ix->h_result, ix->d_result, res_bytes, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1088,6 +1154,15 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
 int yrb_index_search(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w, const uint32_t* mask,
                      int64_t* out_ids, float* out_scores, int32_t* out_counts) {
     return search_host(ix, queries, nq, k, w, nullptr, mask, out_ids, out_scores, out_counts);
+}
+
+int yrb_index_search_ex(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* w, const yrb_where* const* wheres,
+                        const uint32_t* mask, const yrb_search_opts* opts, int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+    if (w && wheres) return fail(YRB_ERR_INVALID, "pass a shared filter or per-query filters, not both");
+    if (wheres && mask) return fail(YRB_ERR_INVALID, "a host bitmask cannot be combined with per-query filters");
+    const float ms = opts ? opts->min_score : -INFINITY;
+    if (ms != ms) return fail(YRB_ERR_INVALID, "min_score is NaN");
+    return search_host(ix, queries, nq, k, w, wheres, mask, out_ids, out_scores, out_counts, ms);
 }
 
 int yrb_index_search_multi(yrb_index* ix, const float* queries, int nq, int k, const yrb_where* const* wheres,
@@ -1178,6 +1253,13 @@ int yrb_index_set_reserved_sms(yrb_index* ix, int n) {
     if (n < 0 || n >= ix->sm_count) return fail(YRB_ERR_INVALID, "reserved SMs must be in [0, %d)", ix->sm_count);
     std::lock_guard<std::mutex> g(ix->mu);
     ix->reserved_sms = n;
+    return YRB_OK;
+}
+
+int yrb_index_cache_stats(const yrb_index* ix, int64_t* out_filter_hits, int64_t* out_compaction_hits) {
+    if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
+    if (out_filter_hits) *out_filter_hits = ix->cache_hits_k4;
+    if (out_compaction_hits) *out_compaction_hits = ix->cache_hits_k8;
     return YRB_OK;
 }
 

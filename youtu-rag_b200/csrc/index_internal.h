@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <string>
@@ -94,6 +95,15 @@ struct yrb_index {
     float* d_cp_sqnorm = nullptr;
     uint32_t* d_cp_map = nullptr;
     int64_t cp_rows_cap = 0;
+    // filter caches (agents repeat the same knowledge-base / source filter).  A key is the hash of
+    // the compiled where program plus `epoch`, which every mutation of rows, tombstones or columns bumps; 0 = no key.
+    uint64_t epoch = 1;
+    uint64_t cur_mask_key = 0;   // key of the mask the current search scans with (set by resolve_mask)
+    uint64_t dmask_key = 0;      // d_mask holds the evaluated mask of this key (K4 skipped on a hit)
+    uint64_t cp_key = 0;         // d_cp_rows / d_cp_map / d_cp_sqnorm hold the compaction of this key (K8 skipped)
+    int64_t cp_pass = 0;
+    bool cp_rowmap = false;
+    int64_t cache_hits_k4 = 0, cache_hits_k8 = 0;
     unsigned long long* h_pass = nullptr;  // pinned
     uint64_t* d_rowkeys = nullptr;  // K6: one key per row, allocated on first use
     int64_t rowkeys_cap = 0;
@@ -141,7 +151,8 @@ int upload_user_mask(yrb_index* ix, const uint32_t* mask, const uint32_t** out, 
 // raw fp32 queries [nq, dim] on the device → nq*k keys (and ids/scores/counts when given).  With `xs` the kernel that
 // finishes a query hands its k keys to the cross-shard merge instead (xshard.cuh) and ids/scores/counts are ignored.
 int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t* mask, int64_t mask_q_stride, uint64_t* out_keys,
-                int64_t* ids, float* scores, int32_t* counts, cudaStream_t st, const yrb::XShard* xs = nullptr);
+                int64_t* ids, float* scores, int32_t* counts, cudaStream_t st, const yrb::XShard* xs = nullptr,
+                float min_score = -INFINITY);   // keep hits with score >= min_score
 // makes column `col` exist (all rows absent) so that a where program naming it compiles on this shard too
 int ensure_column(yrb_index* ix, int col, int col_type);
 

@@ -304,7 +304,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 
     WarpList<KPL> list;
     list.clear();
-    uint64_t thr = 0;
+    // a score threshold (base_retriever.py:71: keep hits with score >= threshold) is the initial bound of every warp's
+    // list: rows below it never enter a list, so the merges and the count see only qualifying hits
+    const uint64_t floor_key = out.floor_key;
+    uint64_t thr = floor_key;
 
     auto offer = [&](const int64_t (&rid)[K1_R], const bool (&va)[K1_R], const float (&acc)[K1_R]) {
 #pragma unroll
@@ -315,7 +318,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                 const uint64_t key = make_key(s, (uint32_t)rid[r]);
                 if (key > thr) {
                     list.insert(key, lane);
-                    thr = list.at(k - 1);
+                    const uint64_t kth = list.at(k - 1);
+                    thr = kth > floor_key ? kth : floor_key;
                 }
             }
         }
@@ -514,7 +518,7 @@ template <bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
     k1q_scan_f32(const uint4* __restrict__ rows, int64_t n_rows, int ld16, int nch, const float4* __restrict__ q_prep,
                  int nq, const float* __restrict__ q_sqn, const float* __restrict__ row_sqnorm, int l2,
-                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ part_keys) {
+                 const uint32_t* __restrict__ mask, int k, uint64_t* __restrict__ part_keys, uint64_t floor_key) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sq = reinterpret_cast<float4*>(smem_raw);  // [K1Q_NQ][nch*32] float4, zero for missing queries / padding
     const int lane = threadIdx.x & 31;
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 #pragma unroll
     for (int qi = 0; qi < K1Q_NQ; ++qi) {
         list[qi].clear();
-        thr[qi] = 0ull;
+        thr[qi] = floor_key;
     }
     const int64_t gw = (int64_t)blockIdx.x * K1_WARPS + warp;
     const int64_t tw = (int64_t)gridDim.x * K1_WARPS;
@@ -592,7 +596,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
                     const uint64_t key = make_key(sc, (uint32_t)rid[r]);
                     if (key > thr[qi]) {
                         list[qi].insert(key, lane);
-                        thr[qi] = list[qi].at(k - 1);
+                        const uint64_t kth = list[qi].at(k - 1);
+                        thr[qi] = kth > floor_key ? kth : floor_key;
                     }
                 }
             }
@@ -619,7 +624,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
 
 cudaError_t launch_k1q_f32(const void* rows, int64_t n_rows, int ld, const float* q_prep, int nq, const float* q_sqn,
                            const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
-                           int sm_count, cudaStream_t st) {
+                           int sm_count, cudaStream_t st, uint64_t floor_key) {
     if (nq < 1 || nq > K1Q_NQ || k < 1 || k > K1_RANK_K) return cudaErrorInvalidValue;
     const int ld16 = ld * 4 / 16;
     const int nch = (ld16 + 31) / 32;
@@ -634,7 +639,7 @@ cudaError_t launch_k1q_f32(const void* rows, int64_t n_rows, int ld, const float
             if (e != cudaSuccess) return e;
         }
         kern<<<grid, K1_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(rows), n_rows, ld16, nch,
-                                             reinterpret_cast<const float4*>(q_prep), nq, q_sqn, row_sqnorm, l2, mask, k, part_keys);
+                                             reinterpret_cast<const float4*>(q_prep), nq, q_sqn, row_sqnorm, l2, mask, k, part_keys, floor_key);
         return cudaGetLastError();
     };
     return mask ? launch(k1q_scan_f32<true>) : launch(k1q_scan_f32<false>);
@@ -647,7 +652,7 @@ template <bool F32, bool HAS_MASK>
 __global__ void __launch_bounds__(K1_THREADS, 1)
     k6_scores(const uint4* __restrict__ rows, int64_t n_rows, int dim, int ld, int ld16, int nch,
               const float* __restrict__ q_raw, int normalize, const float* __restrict__ row_sqnorm, int l2,
-              const uint32_t* __restrict__ mask, uint64_t* __restrict__ keys_out) {
+              const uint32_t* __restrict__ mask, uint64_t* __restrict__ keys_out, uint64_t floor_key) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* sq = reinterpret_cast<float4*>(smem_raw);
     const int lane = threadIdx.x & 31;
@@ -678,7 +683,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1)
             for (int r = 0; r < K1_R; ++r)
                 if (lane == r && va[r])
                     key = make_key(l2 ? fmaf(2.f, acc[r], l2_bias - row_sqnorm[rid[r]]) : acc[r], (uint32_t)row);
-            if (row < n_rows) keys_out[row] = key;
+            if (row < n_rows) keys_out[row] = key > floor_key ? key : 0ull;   // below the score threshold = hidden
         }
     }
 }
@@ -742,7 +747,7 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
 
 cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                           const float* row_sqnorm, int metric, const uint32_t* mask, uint64_t* keys_out, int sm_count,
-                          cudaStream_t st) {
+                          cudaStream_t st, uint64_t floor_key) {
     const int ld16 = ld * elem_size(dtype) / 16;
     const int nch = (ld16 + 31) / 32;
     const size_t smem = (size_t)nch * 32 * (dtype == 1 ? 1 : 2) * sizeof(float4);
@@ -756,7 +761,7 @@ cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, 
             if (e != cudaSuccess) return e;                                                                     \
         }                                                                                                       \
         kern<<<sm_count, K1_THREADS, smem, st>>>(r4, n_rows, dim, ld, ld16, nch, q_raw, normalize, row_sqnorm, l2, \
-                                                 mask, keys_out);                                               \
+                                                 mask, keys_out, floor_key);                                    \
         return cudaGetLastError();                                                                              \
     }
     if (dtype == 1) {

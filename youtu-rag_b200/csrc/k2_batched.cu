@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                  float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
                  int64_t mask_q_stride, const uint32_t* __restrict__ rowmap, float* __restrict__ thr_out,
-                 unsigned int* __restrict__ sync_ctr) {
+                 unsigned int* __restrict__ sync_ctr, float score_floor) {
     constexpr int S = stages(QB);
     constexpr int SB = stage_bytes(QB);
     constexpr int ACC_COLS = QB * BLOCK_R;  // TMEM columns per accumulator buffer
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
         const int64_t slot = (int64_t)blockIdx.x * MAX_Q + qi;
         uint64_t* buf_keys = cand_keys + slot * CAP;
         int cnt = active ? cand_cnt[slot] : 0;
-        float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
+        // score_floor: one ulp below the caller's score threshold (keep hits with score >= threshold), -inf = none
+        float thr = fmaxf((active && thr_init) ? thr_init[qi] : -INFINITY, score_floor);
         if (!active) thr = INFINITY;
         float tops_l[MAX_TOPS];
 #pragma unroll
@@ -241,9 +243,9 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
                     else epi_append(v, mw, thr, r0, buf_keys, cnt);
                 }
                 if (pass == 0)
-                    thr = epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, (int)gridDim.x, 1, k, nq, qi, active,
-                                                  (int)blockIdx.x * 4 * QB + ew, (int)gridDim.x * 4 * QB, 128 * QB,
-                                                  threadIdx.x == 128, lane);
+                    thr = fmaxf(score_floor, epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, (int)gridDim.x, 1, k, nq, qi,
+                                                                     active, (int)blockIdx.x * 4 * QB + ew, (int)gridDim.x * 4 * QB,
+                                                                     128 * QB, threadIdx.x == 128, lane));
             }
             tc_fence_before();
             __syncwarp();
@@ -345,7 +347,7 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
                                int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* mask,
                                const float* thr, uint64_t* ck, int* cc, float* tops, int m_tops, const float* q_sqnorm,
                                const float* row_sqnorm, int64_t mask_q_stride, const uint32_t* rowmap, float* thr_out,
-                               unsigned int* sync_ctr, cudaStream_t st) {
+                               unsigned int* sync_ctr, float score_floor, cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
     auto kern = k2::k2_gemm_topk<QB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -365,7 +367,7 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     cfg.attrs = at;
     cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
-                              q_sqnorm, row_sqnorm, mask_q_stride, rowmap, thr_out, sync_ctr);
+                              q_sqnorm, row_sqnorm, mask_q_stride, rowmap, thr_out, sync_ctr, score_floor);
 }
 
 // CTA-pair kernel for 129..256-query chunks — the default since round 2 (C3: 0.383 ms against 0.449 ms for the
@@ -394,10 +396,12 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               const float* row_sqnorm, uint64_t* out_keys, int64_t* out_ids, float* out_scores, int32_t* out_counts, int sm_count, cudaStream_t st,
               int* launches, std::string& err,
               cudaEvent_t ev_start, cudaEvent_t ev_stop, bool force_pair, const uint32_t* rowmap, int64_t matrix_rows,
-              const XShard* xs_in) {
+              const XShard* xs_in, float min_score) {
     (void)capacity; (void)dim;
     if (rowmap) force_pair = false;  // the row-subset producer lives in the one-CTA kernel
     const float* xn = metric == YRB_METRIC_L2 ? row_sqnorm : nullptr;
+    // the epilogue keeps scores strictly above its bound: one ulp below the threshold keeps score == threshold
+    const float score_floor = (min_score > -INFINITY) ? nextafterf(min_score, -INFINITY) : -INFINITY;
     if (!s->encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -474,7 +478,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             const float* thr2 = nullptr;
             if (sampled2 && !fuse) {
                 K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, 1, nqc, k, mask, mask_q_stride, nullptr, s->cand_keys,
-                                      s->cand_cnt, s->tops, m_tops2, qn, xn, nullptr, nullptr, st));
+                                      s->cand_cnt, s->tops, m_tops2, qn, xn, nullptr, nullptr, score_floor, st));
                 k2::k2_threshold_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(s->tops, n_pairs, m_tops2, k, s->thr0, 2, nqc);
                 K2CK(cudaGetLastError());
                 *launches += 2;
@@ -485,7 +489,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             {
                 cudaError_t e = launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, iters2, nqc, k, mask, mask_q_stride, thr2, s->cand_keys,
                                                  s->cand_cnt, fz ? s->tops : nullptr, fz ? m_tops2 : 0, qn, xn, fz ? s->thr0 : nullptr,
-                                                 fz ? sync_ctr : nullptr, st);
+                                                 fz ? sync_ctr : nullptr, score_floor, st);
                 if (e != cudaSuccess && fz) {  // cooperative launch refused: redo this chunk with the separate sampling pass
                     fprintf(stderr, "yrb200: cooperative launch of k2_gemm_topk_pair refused (%s); sampling runs as separate launches\n",
                             cudaGetErrorString(e));
@@ -513,9 +517,9 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             return YRB_ERR_CUDA;
         auto gemm = [&](int it, const float* thr, float* tops, int m, float* thr_out, unsigned int* ctr) -> cudaError_t {
             return QB == 2 ? launch_gemm<2>(grid, cluster, mq, mr, n_rows, kblocks, 0, it, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
-                                            tops, m, qn, xn, mask_q_stride, rowmap, thr_out, ctr, st)
+                                            tops, m, qn, xn, mask_q_stride, rowmap, thr_out, ctr, score_floor, st)
                            : launch_gemm<1>(grid, cluster, mq, mr, n_rows, kblocks, 0, it, nqc, k, mask, thr, s->cand_keys, s->cand_cnt,
-                                            tops, m, qn, xn, mask_q_stride, rowmap, thr_out, ctr, st);
+                                            tops, m, qn, xn, mask_q_stride, rowmap, thr_out, ctr, score_floor, st);
         };
         // sampling: each CTA's first tile publishes its best scores per query (CTAs past the last tile publish -inf)
         const int gridA = tiles < grid ? tiles : grid;   // CTAs that see a real tile

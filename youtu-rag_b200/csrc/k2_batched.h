@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
 #include <string>
 
 namespace yrb {
@@ -22,7 +23,8 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
               // row-subset mode: `rows` is the whole matrix of matrix_rows rows, n_rows counts the entries of
               // rowmap (padded to a multiple of 128 with valid rows); returned keys carry compact indices
               const uint32_t* rowmap = nullptr, int64_t matrix_rows = 0,
-              const struct XShard* xs = nullptr);  // sharded collection: K3 hands each query's keys to the cross-shard merge
+              const struct XShard* xs = nullptr,   // sharded collection: K3 hands each query's keys to the cross-shard merge
+              float min_score = -INFINITY);        // keep hits with score >= min_score (base_retriever.py:71)
 
 // pair kernel (k2_pair.cu)
 }  // namespace yrb
@@ -31,5 +33,5 @@ namespace yrb {
 cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks, int iters,
                              int nq, int k, const uint32_t* mask, int64_t mask_q_stride, const float* thr, uint64_t* ck,
                              int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm,
-                             float* thr_out, unsigned int* sync_ctr, cudaStream_t st);
+                             float* thr_out, unsigned int* sync_ctr, float score_floor, cudaStream_t st);
 }  // namespace yrb

@@ -62,7 +62,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                       int kblocks, int iters, int nq, int k, const uint32_t* __restrict__ mask, int64_t mask_q_stride,
                       const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                       float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm,
-                      const float* __restrict__ row_sqnorm, float* __restrict__ thr_out, unsigned int* __restrict__ sync_ctr) {
+                      const float* __restrict__ row_sqnorm, float* __restrict__ thr_out, unsigned int* __restrict__ sync_ctr,
+                      float score_floor) {
     constexpr int S = PAIR_STAGES;
     constexpr int ACC_COLS = PAIR_N;  // per buffer; two buffers = all 512 columns
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -165,7 +166,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         const int64_t slot = (int64_t)blockIdx.x * MAX_Q + qi;
         uint64_t* buf_keys = cand_keys + slot * CAP;
         int cnt = active ? cand_cnt[slot] : 0;
-        float thr = (active && thr_init) ? thr_init[qi] : -INFINITY;
+        float thr = fmaxf((active && thr_init) ? thr_init[qi] : -INFINITY, score_floor);   // score_floor: see k2_batched.cu
         if (!active) thr = INFINITY;
         float tops_l[MAX_TOPS];
 #pragma unroll
@@ -202,8 +203,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
                     else epi_append(v, mw, thr, r0, buf_keys, cnt);
                 }
                 if (pass == 0)   // CTA 2i + r published for the queries [128r, 128r + 128): n_pairs publishers per query
-                    thr = epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, n_pairs, 2, k, nq, qi, active,
-                                                  (int)blockIdx.x * 4 + quarter, (int)gridDim.x * 4, 128, threadIdx.x == 128, lane);
+                    thr = fmaxf(score_floor, epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, n_pairs, 2, k, nq, qi, active,
+                                                                     (int)blockIdx.x * 4 + quarter, (int)gridDim.x * 4, 128,
+                                                                     threadIdx.x == 128, lane));
             }
             tc_fence_before();
             __syncwarp();
@@ -238,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks, int iters,
                              int nq, int k, const uint32_t* mask, int64_t mask_q_stride, const float* thr, uint64_t* ck,
                              int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm,
-                             float* thr_out, unsigned int* sync_ctr, cudaStream_t st) {
+                             float* thr_out, unsigned int* sync_ctr, float score_floor, cudaStream_t st) {
     const size_t smem = (size_t)k2::PAIR_STAGES * k2::PAIR_STAGE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(k2::k2_gemm_topk_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -253,7 +255,7 @@ cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap&
     cfg.attrs = at;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, k2::k2_gemm_topk_pair, mq, mr, n_rows, kblocks, iters, nq, k, mask, mask_q_stride, thr, ck, cc,
-                              tops, m_tops, q_sqnorm, row_sqnorm, thr_out, sync_ctr);
+                              tops, m_tops, q_sqnorm, row_sqnorm, thr_out, sync_ctr, score_floor);
 }
 
 }  // namespace yrb

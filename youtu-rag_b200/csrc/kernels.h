@@ -40,7 +40,10 @@ struct K1Out {
     unsigned long long* trace = nullptr;  // optional [grid][8] phase stamps (globaltimer ns), YRB_K1_TRACE
     int use_xs = 0;                       // sharded collection: the last CTA hands the keys to the cross-shard merge
     XShard xs{};
+    uint64_t floor_key = 0;               // score threshold as a key: only keys above it are hits (0 = none)
 };
+// key every qualifying hit exceeds: score >= min_score  <=>  key > score_floor_key(min_score); -inf / NaN → 0 (no threshold)
+uint64_t score_floor_key(float min_score);
 cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                       const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
                       unsigned int* ticket, K1Out out, bool* fused, int sm_count, cudaStream_t st,
@@ -52,7 +55,7 @@ cudaError_t launch_k1(const void* rows, int dtype, int64_t n_rows, int dim, int 
 constexpr int K1Q_MAX_Q = 4, K1Q_MAX_K = 32;
 cudaError_t launch_k1q_f32(const void* rows, int64_t n_rows, int ld, const float* q_prep, int nq, const float* q_sqn,
                            const float* row_sqnorm, int metric, const uint32_t* mask, int k, uint64_t* part_keys,
-                           int sm_count, cudaStream_t st);
+                           int sm_count, cudaStream_t st, uint64_t floor_key = 0);
 
 // ---- K3: selection / merge
 // sorted top-k of unsorted candidates gathered from n_seg segments per query (see k3_select.cu):
@@ -112,7 +115,7 @@ cudaError_t launch_compact_remap(const uint32_t* rowmap, int64_t n, uint64_t* ke
 // ---- K6: any-k path (k <= 4096).  One 64-bit key per row for one query + radix select of the top k.
 cudaError_t launch_scores(const void* rows, int dtype, int64_t n_rows, int dim, int ld, const float* q_raw,
                           const float* row_sqnorm, int metric,
-                          const uint32_t* mask, uint64_t* keys_out, int sm_count, cudaStream_t st);
+                          const uint32_t* mask, uint64_t* keys_out, int sm_count, cudaStream_t st, uint64_t floor_key = 0);
 size_t select_scratch_bytes(int64_t n_rows, int k);
 cudaError_t launch_select(const uint64_t* keys, int64_t n_rows, int k, uint64_t* out_keys,
                           void* scratch, int sm_count, cudaStream_t st);

@@ -37,6 +37,7 @@ struct SearchJob {
     const uint32_t* mask = nullptr;               // caller's host bitmask in GLOBAL row order (or NULL)
     uint32_t active_mask = 0;
     int n_active = 0;
+    float min_score = -INFINITY;
 };
 
 }  // namespace
@@ -154,7 +155,7 @@ int shard_search(yrb_sharded* sh, int s) {
     xs.block_shift = sh->block_shift;
     xs.k = j.ke;
     xs.q0 = 0;
-    return scan_select(ix, ix->d_qf32, j.nq, k_s, m, m_stride, ix->d_keys, nullptr, nullptr, nullptr, st, &xs);
+    return scan_select(ix, ix->d_qf32, j.nq, k_s, m, m_stride, ix->d_keys, nullptr, nullptr, nullptr, st, &xs, j.min_score);
 }
 
 void worker_main(yrb_sharded* sh, int s) {
@@ -247,7 +248,7 @@ int poll_errors(yrb_sharded* sh) {
 }
 
 int sharded_search(yrb_sharded* sh, const float* queries, int nq, int k, const yrb_where* w, const yrb_where* const* per_query,
-                   const uint32_t* mask, int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+                   const uint32_t* mask, int64_t* out_ids, float* out_scores, int32_t* out_counts, float min_score = -INFINITY) {
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (nq < 1 || !queries) return fail(YRB_ERR_INVALID, "need at least one query");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
@@ -281,6 +282,7 @@ int sharded_search(yrb_sharded* sh, const float* queries, int nq, int k, const y
     j.w = w;
     j.per_query = per_query;
     j.mask = mask;
+    j.min_score = min_score;
     for (int s = 0; s < sh->n; ++s)
         if (sh->shard[s]->rows > 0) {
             j.active_mask |= 1u << s;
@@ -661,6 +663,15 @@ int yrb_sharded_search_multi(yrb_sharded* sh, const float* queries, int nq, int 
                              int64_t* out_ids, float* out_scores, int32_t* out_counts) {
     if (!wheres) return fail(YRB_ERR_INVALID, "wheres is NULL (use yrb_sharded_search for a shared filter)");
     return sharded_search(sh, queries, nq, k, nullptr, wheres, nullptr, out_ids, out_scores, out_counts);
+}
+
+int yrb_sharded_search_ex(yrb_sharded* sh, const float* queries, int nq, int k, const yrb_where* w, const yrb_where* const* wheres,
+                          const uint32_t* mask, const yrb_search_opts* opts, int64_t* out_ids, float* out_scores, int32_t* out_counts) {
+    if (w && wheres) return fail(YRB_ERR_INVALID, "pass a shared filter or per-query filters, not both");
+    if (wheres && mask) return fail(YRB_ERR_INVALID, "a host bitmask cannot be combined with per-query filters");
+    const float ms = opts ? opts->min_score : -INFINITY;
+    if (ms != ms) return fail(YRB_ERR_INVALID, "min_score is NaN");
+    return sharded_search(sh, queries, nq, k, w, wheres, mask, out_ids, out_scores, out_counts, ms);
 }
 
 int yrb_sharded_stats(const yrb_sharded* sh, int64_t* out_kernel_launches, int64_t* out_searches) {

@@ -31,15 +31,15 @@ EXPORTS = (
     "yrb_abi_version", "yrb_last_error", "yrb_device_count", "yrb_index_create", "yrb_index_destroy",
     "yrb_index_reserve", "yrb_index_count", "yrb_index_info", "yrb_index_append_host_f32",
     "yrb_index_append_device_f32", "yrb_index_read_rows", "yrb_index_read_raw", "yrb_index_append_raw", "yrb_index_set_live", "yrb_index_clear", "yrb_index_truncate",
-    "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_multi", "yrb_index_search_device",
+    "yrb_index_column_write", "yrb_index_where", "yrb_index_search", "yrb_index_search_ex", "yrb_index_search_multi", "yrb_index_search_device",
     "yrb_index_search_device_ids",
     "yrb_merge_topk_device", "yrb_exchange_handle_bytes", "yrb_exchange_last_error", "yrb_exchange_create",
     "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_search", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_set_reserved_sms", "yrb_index_stats", "yrb_index_profile",
-    "yrb_index_profile_read",
+    "yrb_index_profile_read", "yrb_index_cache_stats",
     "yrb_sharded_create", "yrb_sharded_destroy", "yrb_sharded_count", "yrb_sharded_info", "yrb_sharded_shard",
     "yrb_sharded_append_host_f32", "yrb_sharded_append_device_f32", "yrb_sharded_read_rows", "yrb_sharded_read_raw",
     "yrb_sharded_append_raw", "yrb_sharded_set_live", "yrb_sharded_truncate", "yrb_sharded_clear",
-    "yrb_sharded_column_write", "yrb_sharded_where", "yrb_sharded_search", "yrb_sharded_search_multi", "yrb_sharded_stats",
+    "yrb_sharded_column_write", "yrb_sharded_where", "yrb_sharded_search", "yrb_sharded_search_multi", "yrb_sharded_search_ex", "yrb_sharded_stats",
 )
 
 
@@ -59,6 +59,10 @@ class Where(C.Structure):
         ("operands", C.POINTER(C.c_int64)), ("n_operands", C.c_int32),
         ("postfix", C.POINTER(C.c_int32)), ("n_postfix", C.c_int32),
     ]
+
+
+class SearchOpts(C.Structure):
+    _fields_ = [("min_score", C.c_float), ("reserved", C.c_int32 * 7)]
 
 
 _lib = None
@@ -94,6 +98,8 @@ def lib() -> C.CDLL:
     L.yrb_index_column_write.argtypes = [vp, i32, i32, i64, i64, vp, vp]
     L.yrb_index_where.argtypes = [vp, C.POINTER(Where), vp, C.POINTER(i64)]
     L.yrb_index_search.argtypes = [vp, vp, i32, i32, C.POINTER(Where), vp, vp, vp, vp]
+    L.yrb_index_search_ex.argtypes = [vp, vp, i32, i32, C.POINTER(Where), C.POINTER(C.POINTER(Where)), vp, C.POINTER(SearchOpts), vp, vp, vp]
+    L.yrb_sharded_search_ex.argtypes = [vp, vp, i32, i32, C.POINTER(Where), C.POINTER(C.POINTER(Where)), vp, C.POINTER(SearchOpts), vp, vp, vp]
     L.yrb_index_search_multi.argtypes = [vp, vp, i32, i32, C.POINTER(C.POINTER(Where)), vp, vp, vp]
     L.yrb_index_search_device.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.yrb_index_search_device_ids.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
@@ -109,6 +115,7 @@ def lib() -> C.CDLL:
     L.yrb_index_stats.argtypes = [vp, C.POINTER(i64)]
     L.yrb_index_profile.argtypes = [vp, i32]
     L.yrb_index_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.yrb_index_cache_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.yrb_sharded_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, i32, i32, i64, i32]
     L.yrb_sharded_destroy.argtypes = [vp]
     L.yrb_sharded_count.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
@@ -260,10 +267,13 @@ class Index:
         return out, n.value
 
     # ------------------------------------------------------------ search
+    _SEARCH_EX = "yrb_index_search_ex"
+
     def search(self, queries: np.ndarray, k: int, where: CompiledWhere | None = None,
-               mask: np.ndarray | None = None, wheres: list | None = None):
+               mask: np.ndarray | None = None, wheres: list | None = None, min_score: float | None = None):
         """Host buffers in / out.  Returns (ids int64[nq,k] (-1 pad), scores f32[nq,k], counts int32[nq]).
-        `where`: one compiled filter shared by all queries; `wheres`: one (or None) per query."""
+        `where`: one compiled filter shared by all queries; `wheres`: one (or None) per query; `min_score`: keep only
+        hits with score >= min_score (applied inside the scan, base_retriever.py:71)."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -278,18 +288,18 @@ class Index:
                 raise ValueError("pass either a shared filter (where/mask) or per-query filters (wheres)")
             if len(wheres) != nq:
                 raise ValueError(f"expected {nq} per-query filters, got {len(wheres)}")
+        arr = None
+        if wheres is not None:
             arr = (C.POINTER(Where) * nq)(*[C.pointer(w.struct) if w is not None else C.POINTER(Where)() for w in wheres])
-            _ck(lib().yrb_index_search_multi(self._h, q.ctypes.data, nq, k, arr, ids.ctypes.data, scores.ctypes.data,
-                                             counts.ctypes.data))
-            return ids, scores, counts
         mptr = None
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint32)
             if mask.shape[0] < (self.rows + 31) // 32:
                 raise ValueError("mask has fewer than ceil(rows/32) words")
             mptr = mask.ctypes.data
-        _ck(lib().yrb_index_search(self._h, q.ctypes.data, nq, k, C.byref(where.struct) if where else None, mptr,
-                                   ids.ctypes.data, scores.ctypes.data, counts.ctypes.data))
+        opts = SearchOpts(float("-inf") if min_score is None else float(min_score))
+        _ck(getattr(lib(), self._SEARCH_EX)(self._h, q.ctypes.data, nq, k, C.byref(where.struct) if where else None, arr, mptr,
+                                            C.byref(opts), ids.ctypes.data, scores.ctypes.data, counts.ctypes.data))
         return ids, scores, counts
 
     def search_device(self, dev_queries: int, nq: int, k: int, dev_mask: int, dev_out_keys: int, stream: int = 0):
@@ -319,6 +329,12 @@ class Index:
         n = C.c_int64()
         _ck(lib().yrb_index_stats(self._h, C.byref(n)))
         return n.value
+
+    def cache_stats(self) -> tuple[int, int]:
+        """(filter-mask hits, compaction hits) of the per-filter caches."""
+        a, b = C.c_int64(), C.c_int64()
+        _ck(lib().yrb_index_cache_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 class ShardedIndex(Index):
@@ -420,35 +436,7 @@ class ShardedIndex(Index):
         _ck(lib().yrb_sharded_where(self._h, C.byref(where.struct) if where else None, out.ctypes.data, C.byref(n)))
         return out, n.value
 
-    def search(self, queries: np.ndarray, k: int, where: CompiledWhere | None = None,
-               mask: np.ndarray | None = None, wheres: list | None = None):
-        q = np.ascontiguousarray(queries, dtype=np.float32)
-        if q.ndim == 1:
-            q = q[None, :]
-        if q.ndim != 2 or q.shape[1] != self.dim:
-            raise ValueError(f"expected queries of shape [nq, {self.dim}], got {q.shape}")
-        nq = q.shape[0]
-        ids = np.empty((nq, k), dtype=np.int64)
-        scores = np.empty((nq, k), dtype=np.float32)
-        counts = np.empty(nq, dtype=np.int32)
-        if wheres is not None:
-            if where is not None or mask is not None:
-                raise ValueError("pass either a shared filter (where/mask) or per-query filters (wheres)")
-            if len(wheres) != nq:
-                raise ValueError(f"expected {nq} per-query filters, got {len(wheres)}")
-            arr = (C.POINTER(Where) * nq)(*[C.pointer(w.struct) if w is not None else C.POINTER(Where)() for w in wheres])
-            _ck(lib().yrb_sharded_search_multi(self._h, q.ctypes.data, nq, k, arr, ids.ctypes.data, scores.ctypes.data,
-                                               counts.ctypes.data))
-            return ids, scores, counts
-        mptr = None
-        if mask is not None:
-            mask = np.ascontiguousarray(mask, dtype=np.uint32)
-            if mask.shape[0] < (self.rows + 31) // 32:
-                raise ValueError("mask has fewer than ceil(rows/32) words")
-            mptr = mask.ctypes.data
-        _ck(lib().yrb_sharded_search(self._h, q.ctypes.data, nq, k, C.byref(where.struct) if where else None, mptr,
-                                     ids.ctypes.data, scores.ctypes.data, counts.ctypes.data))
-        return ids, scores, counts
+    _SEARCH_EX = "yrb_sharded_search_ex"
 
     def _each_shard(self, fn_name: str, *args) -> None:
         for s in range(len(self.devices)):

@@ -38,13 +38,20 @@ class VectorRetriever(BaseRetriever):
                 out.append(RetrievalResult(chunk=chunk, score=score, rank=i + 1))
         return out
 
+    def _device_threshold(self, threshold: float) -> dict:
+        """f4: a store that can apply the similarity threshold inside its scan gets it (the hits it drops are exactly the
+        ones `_post` would drop: the list is sorted, the threshold cuts its tail, ranks of the kept hits do not move)."""
+        if threshold > 0.0 and getattr(self.vector_store, "supports_score_threshold", False):
+            return {"score_threshold": threshold}
+        return {}
+
     async def retrieve(self, query: str, top_k: int | None = None, **kwargs) -> list[RetrievalResult]:
         top_k = top_k or self.config.top_k
         filters = kwargs.get("filters")
         threshold = kwargs.get("similarity_threshold", self.config.similarity_threshold)
         query_embedding = await self.embedder.embed_query(query)
         results = await self.vector_store.search(
-            query_embedding=query_embedding, top_k=top_k * 2 if self.reranker else top_k, filters=filters)
+            query_embedding=query_embedding, top_k=top_k * 2 if self.reranker else top_k, filters=filters, **self._device_threshold(threshold))
         retrieval_results = self._post(results, threshold)
         if self.reranker and retrieval_results:
             retrieval_results = await self.reranker.rerank(query=query, results=retrieval_results, top_k=top_k)
@@ -60,7 +67,7 @@ class VectorRetriever(BaseRetriever):
         threshold = kwargs.get("similarity_threshold", self.config.similarity_threshold)
         embeddings = [await self.embedder.embed_query(q) for q in queries]
         per_query = await self.vector_store.search_batch(
-            embeddings, top_k=top_k * 2 if self.reranker else top_k, filters=filters)
+            embeddings, top_k=top_k * 2 if self.reranker else top_k, filters=filters, **self._device_threshold(threshold))
         out = []
         for query, results in zip(queries, per_query):
             rr = self._post(results, threshold)

@@ -36,8 +36,21 @@ logger = logging.getLogger(__name__)
 _METRIC_NAMES = ("cosine", "euclidean", "dot")
 
 
+def _threshold_f32(t: float | None) -> float | None:
+    """The smallest float32 >= t: scores are float32, so `score >= t` (t a Python double, base_retriever.py:71) and
+    `score >= this` select exactly the same hits."""
+    if t is None:
+        return None
+    t32 = np.float32(t)
+    if float(t32) < float(t):
+        t32 = np.nextafter(t32, np.float32(np.inf))
+    return float(t32)
+
+
 class B200VectorStore(BaseVectorStore):
     """Exact dense retrieval over a device-resident chunk-embedding matrix."""
+
+    supports_score_threshold = True   # search / search_batch take score_threshold (applied inside the scan)
 
     def __init__(self, config: VectorStoreConfig):
         self.config = config
@@ -224,17 +237,19 @@ class B200VectorStore(BaseVectorStore):
         return [self._make_chunk(r, e) for r, e in zip(rows, embs)]
 
     async def search(self, query_embedding: list[float], top_k: int = 5,
-                     filters: dict[str, Any] | None = None) -> list[tuple[Chunk, float]]:
-        out = await self.search_batch([query_embedding], top_k=top_k, filters=filters)
+                     filters: dict[str, Any] | None = None, score_threshold: float | None = None) -> list[tuple[Chunk, float]]:
+        out = await self.search_batch([query_embedding], top_k=top_k, filters=filters, score_threshold=score_threshold)
         return out[0]
 
     async def search_batch(self, query_embeddings, top_k: int = 5,
-                           filters: dict[str, Any] | list[dict[str, Any] | None] | None = None
-                           ) -> list[list[tuple[Chunk, float]]]:
+                           filters: dict[str, Any] | list[dict[str, Any] | None] | None = None,
+                           score_threshold: float | None = None) -> list[list[tuple[Chunk, float]]]:
         """Q queries in one device pass (the batched entry point VectorRetriever.batch_retrieve uses;
         the reference loops single searches, base_retriever.py:95-99).  `filters` is one filter for all
         queries or a list with one filter (or None) per query — the shape of the text2sql value-linking
-        loop (unified_schemalink_valuelink.py:289-303: same vector, one metadata filter per column)."""
+        loop (unified_schemalink_valuelink.py:289-303: same vector, one metadata filter per column).
+        `score_threshold` (an extension the reference's store does not have): only hits with score >= threshold are
+        returned — the retriever's rule (base_retriever.py:71) applied inside the scan instead of after it."""
         q = np.asarray(query_embeddings, dtype=np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -260,10 +275,10 @@ class B200VectorStore(BaseVectorStore):
                 if key not in cache:
                     cache[key] = self._compile(f)
                 compiled_list.append(cache[key])  # identical filters share one program (evaluated once)
-            ids, scores, counts = self._index.search(q, int(top_k), wheres=compiled_list)
+            ids, scores, counts = self._index.search(q, int(top_k), wheres=compiled_list, min_score=_threshold_f32(score_threshold))
         else:
             compiled = self._compile(filters)
-            ids, scores, counts = self._index.search(q, int(top_k), where=compiled)
+            ids, scores, counts = self._index.search(q, int(top_k), where=compiled, min_score=_threshold_f32(score_threshold))
         results = []
         for j in range(q.shape[0]):
             n = int(counts[j])
