@@ -164,3 +164,16 @@ class FakeIndex:
             counts[j] = qi.shape[0]
             ids[j, :qi.shape[0]], scores[j, :qi.shape[0]] = qi, si
         return ids, scores, counts
+
+
+class FakeShardedIndex(FakeIndex):
+    """Stand-in for native.ShardedIndex: the store sees the same interface and GLOBAL row ids whether a collection lives
+    on one GPU or is dealt over several, so the host logic is exercised with one fake; what the constructor was handed
+    is kept for the tests to look at."""
+
+    def __init__(self, dim: int, metric: str = "cosine", dtype: str = "bf16", devices=(0,), reserve_rows: int = 0, block_rows: int = 0):
+        super().__init__(dim, metric, dtype, int(list(devices)[0]), reserve_rows)
+        self.devices, self.block_rows = [int(d) for d in devices], block_rows
+
+    def info(self) -> dict:
+        return {**super().info(), "n_devices": len(self.devices), "block_rows": self.block_rows or 16384}

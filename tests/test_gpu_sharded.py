@@ -267,3 +267,42 @@ def test_sharded_store_persistence_roundtrip(tmp_path):
                 got = run(b.search(q, 7, {"source": {"$in": ["file0.pdf", "file1.pdf"]}}))
                 assert [(x.id, s, x.metadata) for x, s in got] == [(x.id, s, x.metadata) for x, s in w]
             b.close()
+
+
+def test_back_to_back_searches_of_changing_shape_and_two_threads():
+    """The ticket / gather protocol of the cross-shard finish over many searches whose batch size and k change from one
+    to the next (the per-query tickets must be back at zero every time), also issued from two threads at once (the
+    entry point serialises them): every answer equals the one-GPU index bit for bit."""
+    import threading
+
+    n, d = 40_000, 128
+    x = unit_rows(n, d, 51)
+    single = native.Index(d, "cosine", "bf16", 0, n)
+    single.append(x)
+    rng = np.random.default_rng(6)
+    shapes = [(1, 10), (3, 100), (300, 5), (1, 128), (17, 32), (2, 200), (64, 10)]
+    qs = {s: rng.standard_normal((s[0], d)).astype(np.float32) for s in shapes}
+    want = {s: single.search(qs[s], s[1]) for s in shapes}
+    for devs in device_sets():
+        ix = native.ShardedIndex(d, "cosine", "bf16", devs, block_rows=512)
+        ix.append(x)
+
+        def run_many(seed, errors):
+            order = np.random.default_rng(seed).integers(0, len(shapes), 60)
+            for o in order:
+                s = shapes[o]
+                got = ix.search(qs[s], s[1])
+                if not (np.array_equal(got[0], want[s][0]) and np.array_equal(got[1].view(np.uint32), want[s][1].view(np.uint32))
+                        and np.array_equal(got[2], want[s][2])):
+                    errors.append(s)
+
+        errs: list = []
+        run_many(0, errs)
+        threads = [threading.Thread(target=run_many, args=(t + 1, errs)) for t in range(2)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errs, errs
+        ix.close()
+    single.close()

@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from tests.fake_index import FakeIndex
+from tests.fake_index import FakeIndex, FakeShardedIndex
 from tests.golden_util import replay_memory_scenario, check_memory_outputs
 from youtu_rag_b200 import B200MemoryVectorStore, B200VectorStore, Chunk, VectorStoreConfig, native
 
@@ -18,6 +18,7 @@ from youtu_rag_b200 import B200MemoryVectorStore, B200VectorStore, Chunk, Vector
 @pytest.fixture(autouse=True)
 def _oracle_behind_the_index(monkeypatch):
     monkeypatch.setattr(native, "Index", FakeIndex)
+    monkeypatch.setattr(native, "ShardedIndex", FakeShardedIndex)
 
 
 # the GPU tests of the store, collected here without the gpu mark: same bodies, fake index underneath
@@ -245,3 +246,21 @@ def test_add_is_all_or_nothing_and_numpy_metadata_is_coerced(tmp_path, monkeypat
     assert asyncio.run(r.count()) == 2 and asyncio.run(r.get_by_id("c0")).metadata["n"] == 8
     hits = asyncio.run(r.search(rng.standard_normal(8).tolist(), top_k=10))
     assert sorted(c.id for c, _ in hits) == ["c0", "c1"]
+
+
+def test_devices_in_index_params_select_the_sharded_index(tmp_path):
+    """g1: `index_params.devices` with more than one GPU makes the store build a ShardedIndex over them (same host logic,
+    global row ids); one device — or none — keeps the one-GPU index on that device."""
+    from tests.golden_util import GOLDEN, compare_with_golden, golden_chunks
+
+    s = B200VectorStore(VectorStoreConfig(collection_name="col_dev", persist_directory=str(tmp_path),
+                                          index_params={"storage_dtype": "f32", "devices": [0, 1, 2, 3], "shard_block_rows": 64, "persist": True}))
+    asyncio.run(s.add_chunks(golden_chunks()))
+    assert isinstance(s.index, FakeShardedIndex) and s.index.devices == [0, 1, 2, 3] and s.index.block_rows == 64
+    for rec in GOLDEN["chroma"]:
+        if rec["metric"] == "cosine" and "error" not in rec:
+            compare_with_golden(asyncio.run(s.search(GOLDEN["queries"][rec["query"]], rec["top_k"], rec["filters"])), rec["results"], tol=2e-6)
+    s.close()
+    one = B200VectorStore(VectorStoreConfig(collection_name="col_dev", persist_directory=str(tmp_path),
+                                            index_params={"storage_dtype": "f32", "devices": [2], "persist": True}))
+    assert type(one.index) is FakeIndex and one.index.device == 2 and asyncio.run(one.count()) == len(golden_chunks())   # reloaded
