@@ -306,3 +306,27 @@ def test_back_to_back_searches_of_changing_shape_and_two_threads():
         assert not errs, errs
         ix.close()
     single.close()
+
+
+def test_entry_points_leave_the_callers_device_alone():
+    """The library switches devices internally (a sharded collection walks over several); a caller sharing the thread
+    with torch must find its current device unchanged after every call."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs to tell devices apart")
+    torch.cuda.set_device(1)
+    x = unit_rows(3000, 64, 1)
+    ix = native.ShardedIndex(64, "cosine", "bf16", [0, 1], block_rows=256)
+    ix.append(x)
+    one = native.Index(64, "cosine", "bf16", 0, 3000)
+    one.append(x)
+    for index in (ix, one):
+        index.search(x[:3], 5)
+        index.set_live([1, 2], False)
+        index.read_rows([0, 700])
+        assert torch.cuda.current_device() == 1
+    ix.close()
+    one.close()
+    assert torch.cuda.current_device() == 1
+    torch.cuda.set_device(0)

@@ -724,6 +724,7 @@ int yrb_index_create(yrb_index** out, int device, int dim, int metric, int stora
     if (dim < 1 || dim > 65536) return fail(YRB_ERR_INVALID, "dim %d out of range [1, 65536]", dim);
     if (metric < 0 || metric > 2) return fail(YRB_ERR_INVALID, "unknown metric %d", metric);
     if (storage_dtype < 0 || storage_dtype > 1) return fail(YRB_ERR_INVALID, "unknown storage dtype %d", storage_dtype);
+    DevGuard dev_guard_;
     int n = 0;
     int rc = yrb_device_count(&n);
     if (rc) return rc;
@@ -775,6 +776,7 @@ int yrb_index_create(yrb_index** out, int device, int dim, int metric, int stora
 
 int yrb_index_destroy(yrb_index* ix) {
     if (!ix) return YRB_OK;
+    DevGuard dev_guard_;
     cudaSetDevice(ix->device);
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     free_scratch(ix);
@@ -814,6 +816,7 @@ int yrb_index_destroy(yrb_index* ix) {
 int yrb_index_reserve(yrb_index* ix, int64_t rows) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     return ensure_capacity(ix, rows);
@@ -844,6 +847,7 @@ int yrb_index_append_host_f32(yrb_index* ix, const float* rows, int64_t n) {
     if (n < 0 || (n > 0 && !rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
     if (n == 0) return YRB_OK;
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if (ix->rows + n > 0xfffffffell) return fail(YRB_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
@@ -873,6 +877,7 @@ int yrb_index_append_device_f32(yrb_index* ix, const float* dev_rows, int64_t n,
     if (n < 0 || (n > 0 && !dev_rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
     if (n == 0) return YRB_OK;
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if (ix->rows + n > 0xfffffffell) return fail(YRB_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
@@ -885,6 +890,7 @@ int yrb_index_read_rows(yrb_index* ix, const int64_t* row_ids, int64_t n, float*
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && (!row_ids || !out_rows))) return fail(YRB_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     const size_t es = yrb::elem_size(ix->dtype);
@@ -923,6 +929,7 @@ int yrb_index_read_raw(yrb_index* ix, int64_t row_begin, int64_t n, void* out_ro
     if (n == 0) return YRB_OK;
     if (!out_rows || !out_sqnorm) return fail(YRB_ERR_INVALID, "output buffers are NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     const size_t rb = (size_t)ix->ld * yrb::elem_size(ix->dtype);
@@ -938,6 +945,7 @@ int yrb_index_append_raw(yrb_index* ix, const void* rows, const float* sqnorm, i
     if (n < 0 || (n > 0 && (!rows || !sqnorm))) return fail(YRB_ERR_INVALID, "bad arguments");
     if (n == 0) return YRB_OK;
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if (ix->rows + n > 0xfffffffell) return fail(YRB_ERR_UNSUPPORTED, "more than 2^32-2 rows per GPU shard");
@@ -958,6 +966,7 @@ int yrb_index_set_live(yrb_index* ix, const int64_t* row_ids, int64_t n, int liv
     if (n < 0 || (n > 0 && !row_ids)) return fail(YRB_ERR_INVALID, "bad arguments");
     if (n == 0) return YRB_OK;
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     for (int64_t i = 0; i < n; ++i)
@@ -987,6 +996,7 @@ int yrb_index_truncate(yrb_index* ix, int64_t rows) {
     if (rows < 0 || rows > ix->rows) return fail(YRB_ERR_INVALID, "truncate to %lld rows: index holds %lld", (long long)rows, (long long)ix->rows);
     if (rows == ix->rows) return YRB_OK;
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ix->stream));
@@ -1013,6 +1023,7 @@ int yrb_index_truncate(yrb_index* ix, int64_t rows) {
 int yrb_index_clear(yrb_index* ix) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ix->stream));
@@ -1038,6 +1049,7 @@ int yrb_index_column_write(yrb_index* ix, int col, int col_type, int64_t row_beg
     if (n < 0 || row_begin < 0 || (n > 0 && (!values || !present))) return fail(YRB_ERR_INVALID, "bad arguments");
     if (n == 0) return YRB_OK;
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if (row_begin + n > ix->rows) return fail(YRB_ERR_INVALID, "column rows [%lld,%lld) beyond appended rows %lld",
@@ -1060,6 +1072,7 @@ int yrb_index_where(yrb_index* ix, const yrb_where* w, uint32_t* out_mask, int64
     Nvtx nvtx_("yrb_index_where");
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if (ix->rows == 0) {
@@ -1087,6 +1100,7 @@ static int search_host(yrb_index* ix, const float* queries, int nq, int k, const
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
     if (!out_ids || !out_scores) return fail(YRB_ERR_INVALID, "output buffers are NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     const int64_t live_rows = ix->rows - ix->n_dead;
@@ -1178,6 +1192,7 @@ int yrb_index_search_device(yrb_index* ix, const float* dev_queries, int nq, int
     if (nq < 1 || !dev_queries || !dev_out_keys) return fail(YRB_ERR_INVALID, "bad arguments");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
@@ -1200,6 +1215,7 @@ int yrb_index_search_device_ids(yrb_index* ix, const float* dev_queries, int nq,
         return fail(YRB_ERR_INVALID, "bad arguments");
     if (k < 1) return fail(YRB_ERR_INVALID, "k must be >= 1 (got %d)", k);
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
@@ -1215,6 +1231,7 @@ int yrb_merge_topk_device(int device, const uint64_t* dev_keys, int parts, int n
     if (!dev_keys || !dev_row_base || !dev_out_ids || !dev_out_scores) return fail(YRB_ERR_INVALID, "NULL buffer");
     if (parts < 1 || nq < 1 || k < 1) return fail(YRB_ERR_INVALID, "bad parts/nq/k");
     if ((int64_t)parts * k > 2048) return fail(YRB_ERR_UNSUPPORTED, "parts*k = %lld exceeds 2048", (long long)parts * k);
+    DevGuard dev_guard_;
     CK(cudaSetDevice(device));
     CK(yrb::launch_merge_global(dev_keys, parts, nq, k, dev_row_base, dev_out_ids, dev_out_scores, dev_out_counts,
                                 (cudaStream_t)stream));
@@ -1231,6 +1248,7 @@ int yrb_index_set_path(yrb_index* ix, int path) {
 int yrb_index_profile(yrb_index* ix, int enable) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     ix->prof = enable != 0;
     return YRB_OK;
 }
@@ -1238,6 +1256,7 @@ int yrb_index_profile(yrb_index* ix, int enable) {
 int yrb_index_profile_read(yrb_index* ix, double* out_total_ms, int64_t* out_launches) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if ((rc = prof_flush(ix))) return rc;
@@ -1252,6 +1271,7 @@ int yrb_index_set_reserved_sms(yrb_index* ix, int n) {
     if (!ix) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || n >= ix->sm_count) return fail(YRB_ERR_INVALID, "reserved SMs must be in [0, %d)", ix->sm_count);
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     ix->reserved_sms = n;
     return YRB_OK;
 }

@@ -27,6 +27,25 @@ struct Nvtx {
     Nvtx& operator=(const Nvtx&) = delete;
 };
 
+// Restores the calling thread's current CUDA device when an entry point returns: the library switches to the index's
+// device (and, for a sharded collection, walks over several), and a caller that shares the thread with another CUDA
+// user (torch in the serving process) must find its device unchanged.
+struct DevGuard {
+    int prev = -1;
+    DevGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DevGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
+
 // sets the calling thread's error message (yrb_last_error) and returns `code`
 int fail(int code, const char* fmt, ...);
 const std::string& last_error();

@@ -152,6 +152,7 @@ int yrb_exchange_create(yrb_exchange** out, int device, int world, int rank, int
     if (!out || !out_handles) return xfail(YRB_ERR_INVALID, "NULL argument");
     if (world < 1 || world > 8 || rank < 0 || rank >= world) return xfail(YRB_ERR_INVALID, "world must be 1..8 and rank in range");
     if ((int64_t)world * k_cap > yrb::EX_CAP) return xfail(YRB_ERR_UNSUPPORTED, "world * k exceeds 2048");
+    yrbi::DevGuard dev_guard_;
     if (cudaSetDevice(device) != cudaSuccess) return xfail(YRB_ERR_CUDA, "cudaSetDevice failed");
     yrb_exchange* ex = new yrb_exchange();
     ex->device = device;
@@ -184,6 +185,7 @@ int yrb_exchange_handle_bytes(void) { return 2 * (int)sizeof(cudaIpcMemHandle_t)
 
 int yrb_exchange_connect(yrb_exchange* ex, const unsigned char* all_handles) {
     if (!ex || !all_handles) return xfail(YRB_ERR_INVALID, "NULL argument");
+    yrbi::DevGuard dev_guard_;
     if (cudaSetDevice(ex->device) != cudaSuccess) return xfail(YRB_ERR_CUDA, "cudaSetDevice failed");
     const int hb = yrb_exchange_handle_bytes();
     for (int p = 0; p < ex->world; ++p) {
@@ -211,6 +213,7 @@ int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq,
                        int64_t* dev_out_ids, float* dev_out_scores, int32_t* dev_out_counts, void* stream) {
     if (!ex || !dev_local_keys || !dev_row_base || !dev_out_ids || !dev_out_scores) return xfail(YRB_ERR_INVALID, "NULL argument");
     if (nq < 1 || nq > ex->nq_cap || k < 1 || k > ex->k_cap) return xfail(YRB_ERR_INVALID, "nq / k exceed the exchange's capacity");
+    yrbi::DevGuard dev_guard_;
     if (cudaSetDevice(ex->device) != cudaSuccess) return xfail(YRB_ERR_CUDA, "cudaSetDevice failed");
     yrb::ExArgs a{};
     for (int p = 0; p < ex->world; ++p) {
@@ -248,6 +251,7 @@ int yrb_exchange_search(yrb_exchange* ex, yrb_index* ix, const float* queries, i
     if (ix->device != ex->device) return fail(YRB_ERR_INVALID, "index and exchange live on different devices");
     if (k > ix->rows) return fail(YRB_ERR_INVALID, "k=%d exceeds this shard's rows=%lld", k, (long long)ix->rows);
     std::lock_guard<std::mutex> g(ix->mu);
+    DevGuard dev_guard_;
     int rc = set_dev(ix);
     if (rc) return rc;
     if ((rc = ensure_scratch(ix, nq, k))) return rc;
@@ -275,6 +279,7 @@ int yrb_exchange_search(yrb_exchange* ex, yrb_index* ix, const float* queries, i
 
 int yrb_exchange_destroy(yrb_exchange* ex) {
     if (!ex) return YRB_OK;
+    yrbi::DevGuard dev_guard_;
     cudaSetDevice(ex->device);
     cudaDeviceSynchronize();
     for (int p = 0; p < ex->world; ++p)

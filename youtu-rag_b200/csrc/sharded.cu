@@ -255,6 +255,7 @@ int sharded_search(yrb_sharded* sh, const float* queries, int nq, int k, const y
     if (!out_ids || !out_scores) return fail(YRB_ERR_INVALID, "output buffers are NULL");
     Nvtx nvtx_("yrb_sharded_search");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     int64_t live = 0;
     for (int s = 0; s < sh->n; ++s) live += sh->shard[s]->rows - sh->shard[s]->n_dead;
     auto fill_empty = [&] {
@@ -355,6 +356,7 @@ int yrb_sharded_create(yrb_sharded** out, const int* devices, int n_devices, int
     if (B < 64 || (B & (B - 1))) return fail(YRB_ERR_INVALID, "block_rows must be a power of two >= 64 (got %lld)", (long long)B);
     int shift = 0;
     while ((int64_t(1) << shift) < B) ++shift;
+    DevGuard dev_guard_;
     yrb_sharded* sh = new (std::nothrow) yrb_sharded();
     if (!sh) return fail(YRB_ERR_NOMEM, "host allocation failed");
     sh->n = n_devices;
@@ -403,6 +405,7 @@ int yrb_sharded_create(yrb_sharded** out, const int* devices, int n_devices, int
 
 int yrb_sharded_destroy(yrb_sharded* sh) {
     if (!sh) return YRB_OK;
+    DevGuard dev_guard_;
     bool have_workers = false;
     for (int s = 0; s < sh->n; ++s) have_workers |= sh->workers[s].joinable();
     if (have_workers) {
@@ -464,6 +467,7 @@ int yrb_sharded_append_host_f32(yrb_sharded* sh, const float* rows, int64_t n) {
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && !rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     const int64_t g0 = sh->rows;
     int rc = for_pieces(sh, g0, n, [&](int s, int64_t local, int64_t gb, int64_t cnt) {
         if (sh->shard[s]->rows != local) return fail(YRB_ERR_INVALID, "shard %d holds %lld rows, expected %lld", s, (long long)sh->shard[s]->rows, (long long)local);
@@ -481,6 +485,7 @@ int yrb_sharded_append_device_f32(yrb_sharded* sh, const float* dev_rows, int64_
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && !dev_rows)) return fail(YRB_ERR_INVALID, "bad rows/n");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     const int64_t g0 = sh->rows;
     int rc = for_pieces(sh, g0, n, [&](int s, int64_t local, int64_t gb, int64_t cnt) {
         yrb_index* ix = sh->shard[s];
@@ -513,6 +518,7 @@ int yrb_sharded_read_rows(yrb_sharded* sh, const int64_t* row_ids, int64_t n, fl
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && (!row_ids || !out_rows))) return fail(YRB_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     // runs of consecutive ids inside one block become one read on their shard
     int64_t i = 0;
     while (i < n) {
@@ -538,6 +544,7 @@ int yrb_sharded_read_raw(yrb_sharded* sh, int64_t row_begin, int64_t n, void* ou
     if (n == 0) return YRB_OK;
     if (!out_rows || !out_sqnorm) return fail(YRB_ERR_INVALID, "output buffers are NULL");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     const size_t rb = (size_t)sh->ld * yrb::elem_size(sh->dtype);
     return for_pieces(sh, row_begin, n, [&](int s, int64_t local, int64_t gb, int64_t cnt) {
         return yrb_index_read_raw(sh->shard[s], local, cnt, static_cast<char*>(out_rows) + (size_t)(gb - row_begin) * rb,
@@ -549,6 +556,7 @@ int yrb_sharded_append_raw(yrb_sharded* sh, const void* rows, const float* sqnor
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && (!rows || !sqnorm))) return fail(YRB_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     const int64_t g0 = sh->rows;
     const size_t rb = (size_t)sh->ld * yrb::elem_size(sh->dtype);
     int rc = for_pieces(sh, g0, n, [&](int s, int64_t local, int64_t gb, int64_t cnt) {
@@ -567,6 +575,7 @@ int yrb_sharded_set_live(yrb_sharded* sh, const int64_t* row_ids, int64_t n, int
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (n < 0 || (n > 0 && !row_ids)) return fail(YRB_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     std::vector<int64_t> per[yrb::XS_MAX_SHARDS];
     for (int64_t i = 0; i < n; ++i) {
         if (row_ids[i] < 0 || row_ids[i] >= sh->rows) return fail(YRB_ERR_INVALID, "row id %lld out of range", (long long)row_ids[i]);
@@ -587,6 +596,7 @@ int yrb_sharded_truncate(yrb_sharded* sh, int64_t rows) {
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     if (rows < 0 || rows > sh->rows) return fail(YRB_ERR_INVALID, "truncate to %lld rows: index holds %lld", (long long)rows, (long long)sh->rows);
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     for (int s = 0; s < sh->n; ++s) {
         const int rc = yrb_index_truncate(sh->shard[s], rows_on_shard(sh, rows, s));
         if (rc) return rc;
@@ -598,6 +608,7 @@ int yrb_sharded_truncate(yrb_sharded* sh, int64_t rows) {
 int yrb_sharded_clear(yrb_sharded* sh) {
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     for (int s = 0; s < sh->n; ++s) {
         const int rc = yrb_index_clear(sh->shard[s]);
         if (rc) return rc;
@@ -614,6 +625,7 @@ int yrb_sharded_column_write(yrb_sharded* sh, int col, int col_type, int64_t row
     if (n < 0 || row_begin < 0 || (n > 0 && (!values || !present))) return fail(YRB_ERR_INVALID, "bad arguments");
     if (row_begin + n > sh->rows) return fail(YRB_ERR_INVALID, "column rows beyond appended rows");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     // the column must exist on EVERY shard: the same compiled where program runs on all of them
     for (int s = 0; s < sh->n; ++s) {
         yrb_index* ix = sh->shard[s];
@@ -632,6 +644,7 @@ int yrb_sharded_column_write(yrb_sharded* sh, int col, int col_type, int64_t row
 int yrb_sharded_where(yrb_sharded* sh, const yrb_where* w, uint32_t* out_mask, int64_t* out_pass) {
     if (!sh) return fail(YRB_ERR_INVALID, "index is NULL");
     std::lock_guard<std::mutex> g(sh->mu);
+    DevGuard dev_guard_;
     int64_t pass = 0;
     const int64_t wpb = block_rows(sh) / 32, gw_total = (sh->rows + 31) / 32;
     if (out_mask) memset(out_mask, 0, (size_t)gw_total * 4);
