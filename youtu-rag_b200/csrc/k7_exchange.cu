@@ -67,8 +67,13 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 constexpr int EX_MAX_GRID = 64;
 constexpr long long EX_TIMEOUT_CLK = 120000000000ll;  // ~60 s: a peer that is this late is gone; trap instead of hanging
 
+// CAP = candidates per query this instance can sort.  The small instance (1024 candidates = 16 KiB of shared memory)
+// matters beyond its size: a K2 CTA (197.6 KiB) and a K7 CTA of that size FIT on one SM together, so the cooperative
+// launch of the next search's GEMM does not have to wait until the exchange of the previous one has left every SM it
+// was scattered over (with 32 KiB they do not fit, and 8-GPU 256-query batches lost ~0.15 ms per step to that wait).
+template <int CAP>
 __global__ void __launch_bounds__(EX_THREADS) exchange_merge_kernel(ExArgs a) {
-    __shared__ GKeyX sk[EX_CAP];
+    __shared__ GKeyX sk[CAP];
     __shared__ int cnt;
     const int tid = threadIdx.x;
     const int par = a.epoch & 1u;
@@ -232,7 +237,10 @@ int yrb_exchange_merge(yrb_exchange* ex, const uint64_t* dev_local_keys, int nq,
     a.ids = dev_out_ids;
     a.scores = dev_out_scores;
     a.counts = dev_out_counts;
-    yrb::exchange_merge_kernel<<<std::min(nq, yrb::EX_MAX_GRID), yrb::EX_THREADS, 0, (cudaStream_t)stream>>>(a);
+    if (ex->world * k <= 1024)
+        yrb::exchange_merge_kernel<1024><<<std::min(nq, yrb::EX_MAX_GRID), yrb::EX_THREADS, 0, (cudaStream_t)stream>>>(a);
+    else
+        yrb::exchange_merge_kernel<yrb::EX_CAP><<<std::min(nq, yrb::EX_MAX_GRID), yrb::EX_THREADS, 0, (cudaStream_t)stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return xfail(YRB_ERR_CUDA, std::string("exchange_merge_kernel: ") + cudaGetErrorString(e));
     return YRB_OK;
