@@ -514,7 +514,8 @@ int scan_select(yrb_index* ix, const float* dev_q, int nq, int k, const uint32_t
         std::string err;
         // compacted keys carry compact row numbers until K8 maps them back: the cross-shard finish then runs on its own
         rc = yrb::k2_search(ix->k2, k2_rows, k2_n, ix->capacity, ix->dim, ix->ld, ix->d_q, nq, k, mask,
-                            mask_q_stride, ix->metric, ix->d_qsq, k2_sqnorm, out_keys, ids, scores, counts, sms, st,
+                            mask_q_stride, ix->metric, ix->d_qsq, k2_sqnorm, out_keys, ids, scores, counts,
+                            ix->sm_count & ~1 /* every SM: the exchange kernel's 16 KiB CTAs share an SM with a K2 CTA */, st,
                             &launches, err, ea, eb, pair, (compacted && use_rowmap) ? ix->d_cp_map : nullptr, ix->rows,
                             compacted ? nullptr : xs, min_score);
         if (rc) set_error(err);
