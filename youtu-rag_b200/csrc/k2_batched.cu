@@ -42,8 +42,8 @@ namespace k2 {
 
 // ---------------------------------------------------------------- the kernel
 template <int QB>
-__global__ void __launch_bounds__(128 + 128 * QB, 1)
-    k2_gemm_topk(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows,
+__device__ __forceinline__ void
+    k2_gemm_topk_body(const CUtensorMap& tmap_q, const CUtensorMap& tmap_r, int64_t n_rows,
                  int kblocks, int tile_begin, int iters, int nq, int k, const uint32_t* __restrict__ mask,
                  const float* __restrict__ thr_init, uint64_t* __restrict__ cand_keys, int* __restrict__ cand_cnt,
                  float* __restrict__ tops, int m_tops, const float* __restrict__ q_sqnorm, const float* __restrict__ row_sqnorm,
@@ -274,6 +274,30 @@ __global__ void __launch_bounds__(128 + 128 * QB, 1)
     }
 }
 
+// Two entry points over the same body.  The cluster size is a COMPILE-TIME attribute of the kernel (as in k2_pair.cu):
+// with the cluster dimension passed as a launch attribute next to the cooperative attribute, the launch failed under
+// Nsight Compute (the profiler recorded a (0,0,0) grid and the driver reported LaunchFailed), which would break any
+// tooling that lists the kernels of a run.
+#define YRB_K2_PARAMS                                                                                                       \
+    const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_r, int64_t n_rows, int kblocks,   \
+        int tile_begin, int iters, int nq, int k, const uint32_t *__restrict__ mask, const float *__restrict__ thr_init,    \
+        uint64_t *__restrict__ cand_keys, int *__restrict__ cand_cnt, float *__restrict__ tops, int m_tops,                 \
+        const float *__restrict__ q_sqnorm, const float *__restrict__ row_sqnorm, int64_t mask_q_stride,                    \
+        const uint32_t *__restrict__ rowmap, float *__restrict__ thr_out, unsigned int *__restrict__ sync_ctr, float score_floor
+#define YRB_K2_ARGS                                                                                                          \
+    tmap_q, tmap_r, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr_init, cand_keys, cand_cnt, tops, m_tops, q_sqnorm,  \
+        row_sqnorm, mask_q_stride, rowmap, thr_out, sync_ctr, score_floor
+template <int QB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * QB, 1) k2_gemm_topk(YRB_K2_PARAMS) {
+    k2_gemm_topk_body<QB>(YRB_K2_ARGS);
+}
+template <int QB>
+__global__ void __launch_bounds__(128 + 128 * QB, 1) k2_gemm_topk_c1(YRB_K2_PARAMS) {
+    k2_gemm_topk_body<QB>(YRB_K2_ARGS);
+}
+#undef YRB_K2_PARAMS
+#undef YRB_K2_ARGS
+
 // ---------------------------------------------------------------- thresholds from phase A
 // thr0[q] = k-th largest of the (n_cta * m) published best scores: every one is the score of a distinct
 // real row, so at least k rows score >= thr0[q] and thr0[q] <= the true k-th best.  Fewer than k → -inf.
@@ -349,7 +373,7 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
                                const float* row_sqnorm, int64_t mask_q_stride, const uint32_t* rowmap, float* thr_out,
                                unsigned int* sync_ctr, float score_floor, cudaStream_t st) {
     const size_t smem = (size_t)k2::stages(QB) * k2::stage_bytes(QB) + 1024;
-    auto kern = k2::k2_gemm_topk<QB>;
+    auto kern = cluster == 2 ? k2::k2_gemm_topk<QB> : k2::k2_gemm_topk_c1<QB>;   // cluster of 2 (compile-time) or none
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -357,15 +381,11 @@ static cudaError_t launch_gemm(int grid, int cluster, const CUtensorMap& mq, con
     cfg.blockDim = dim3(128 + 128 * QB);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cluster;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    at[1].id = cudaLaunchAttributeCooperative;   // the fused sampling meets grid-wide: every CTA must be resident
-    at[1].val.cooperative = thr_out != nullptr ? 1 : 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // the fused sampling meets grid-wide: every CTA must be resident
+    at[0].val.cooperative = thr_out != nullptr ? 1 : 0;
     cfg.attrs = at;
-    cfg.numAttrs = 2;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, mq, mr, n_rows, kblocks, tile_begin, iters, nq, k, mask, thr, ck, cc, tops, m_tops,
                               q_sqnorm, row_sqnorm, mask_q_stride, rowmap, thr_out, sync_ctr, score_floor);
 }
@@ -379,16 +399,16 @@ static bool k2_use_pair(bool forced) {
     return forced || v != 0;
 }
 
-// cluster size for the query multicast: 2 always packs the 148 SMs (74 TPCs); override with YRB_K2_CLUSTER
+// cluster size for the query multicast: 2 (always packs the 148 SMs: 74 TPCs) or, with YRB_K2_CLUSTER=1, none.
+// (4 was measured in round 1 — 0.87 ms against 0.50: it strands SMs — and is no longer selectable: the cluster size
+// is a compile-time attribute of the kernel now.)
 static int k2_cluster(int grid) {
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("YRB_K2_CLUSTER");
         forced = e ? atoi(e) : 0;
     }
-    int c = forced > 0 ? forced : 2;
-    while (c > 1 && grid % c) c >>= 1;
-    return c;
+    return (forced == 1 || grid % 2) ? 1 : 2;
 }
 
 int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, int dim, int ld, const void* q, int nq,

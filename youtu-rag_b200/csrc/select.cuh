@@ -210,6 +210,25 @@ __device__ __forceinline__ void select_topk_block(const SelectArgs& a, const int
     }
 
     const int n = n_all;
+    if (n <= SEL_THREADS) {
+        // ---- few candidates (small collections, tight bounds): rank by counting — candidate t's output slot is the
+        // number of keys above it (keys are unique), one pass over shared memory, no histogram rounds, no sort.
+        // A 16-query batch over 10k rows spent 16 us per selection in the general path for ~30 candidates.
+        const uint64_t mine = tid < n ? sk[tid] : 0ull;
+        int rank = 0;
+        for (int j = 0; j < n; ++j) rank += sk[j] > mine;
+        __syncthreads();                      // every thread has read sk; sel (and, for xshard, sk) may be written now
+        const int cnt = n < k ? n : k;
+        if (tid < n && rank < k) sel[rank] = mine;
+        __syncthreads();
+        if (a.use_xs) {
+            xshard_finish(a.xs, q, sel, cnt, sk);
+            return;
+        }
+        for (int i = tid; i < k; i += SEL_THREADS) select_emit(a, q, i, (i < cnt) ? sel[i] : 0ull);
+        if (tid == 0 && a.out_counts) a.out_counts[q] = cnt;
+        return;
+    }
     int need = n < k ? n : k;
     if (n > k) {
         // ---- key range
