@@ -68,9 +68,8 @@ constexpr int EX_MAX_GRID = 64;
 constexpr long long EX_TIMEOUT_CLK = 120000000000ll;  // ~60 s: a peer that is this late is gone; trap instead of hanging
 
 // CAP = candidates per query this instance can sort.  The small instance (1024 candidates = 16 KiB of shared memory)
-// matters beyond its size: a K2 CTA (197.6 KiB) and a K7 CTA of that size FIT on one SM together, so the cooperative
-// launch of the next search's GEMM does not have to wait until the exchange of the previous one has left every SM it
-// was scattered over (with 32 KiB they do not fit, and 8-GPU 256-query batches lost ~0.15 ms per step to that wait).
+// fits on an SM beside a K2 CTA (197.6 KiB), the large one does not; with world <= 8 and k <= 128 the small one is always
+// enough.  (Measured: no effect on 8-GPU batch steps — the co-residency was not what limited them)
 template <int CAP>
 __global__ void __launch_bounds__(EX_THREADS) exchange_merge_kernel(ExArgs a) {
     __shared__ GKeyX sk[CAP];
