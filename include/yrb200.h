@@ -225,6 +225,11 @@ YRB_API int yrb_exchange_destroy(yrb_exchange* ex);
  * writes the result into pinned host memory).  Every entry mirrors its yrb_index_* namesake and works in GLOBAL row
  * ids.  Peer access between the first device and the others is required (YRB_ERR_UNSUPPORTED otherwise). */
 typedef struct yrb_sharded yrb_sharded;
+/* the row map itself (stateless; needs no GPU): where a global row lives, the global row of a shard's local row — the
+ * function the merge kernels apply —, and how many rows a shard holds when the collection has total_rows */
+YRB_API int yrb_shard_locate(int n_shards, int block_rows, int64_t global_row, int* out_shard, int64_t* out_local);
+YRB_API int yrb_shard_global(int n_shards, int block_rows, int shard, int64_t local_row, int64_t* out_global);
+YRB_API int yrb_shard_rows(int n_shards, int block_rows, int64_t total_rows, int shard, int64_t* out_rows);
 YRB_API int yrb_sharded_create(yrb_sharded** out, const int* devices, int n_devices /* 1..8 */, int dim, int metric,
                                int storage_dtype, int64_t reserve_rows, int block_rows /* 0 = 16384; power of two >= 64 */);
 YRB_API int yrb_sharded_destroy(yrb_sharded* sh);

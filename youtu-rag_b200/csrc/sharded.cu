@@ -83,15 +83,12 @@ inline int64_t block_rows(const yrb_sharded* sh) { return int64_t(1) << sh->bloc
 
 // rows shard s holds when the collection has `total` rows
 int64_t rows_on_shard(const yrb_sharded* sh, int64_t total, int s) {
-    const int64_t B = block_rows(sh), nb = total >> sh->block_shift, rem = total & (B - 1);
-    int64_t r = (nb / sh->n + (s < nb % sh->n ? 1 : 0)) << sh->block_shift;
-    if (s == nb % sh->n) r += rem;
+    int64_t r = 0;
+    yrb_shard_rows(sh->n, (int)block_rows(sh), total, s, &r);
     return r;
 }
 inline void locate(const yrb_sharded* sh, int64_t g, int* s, int64_t* local) {
-    const int64_t b = g >> sh->block_shift;
-    *s = (int)(b % sh->n);
-    *local = ((b / sh->n) << sh->block_shift) | (g & (block_rows(sh) - 1));
+    yrb_shard_locate(sh->n, (int)block_rows(sh), g, s, local);
 }
 // [g0, g0 + n) cut at block boundaries: fn(shard, local_begin, global_begin, count) → rc
 template <class Fn>
@@ -343,6 +340,35 @@ int sharded_search(yrb_sharded* sh, const float* queries, int nq, int k, const y
 }  // namespace
 
 extern "C" {
+
+// ---- the block-cyclic row map, stateless (also what tests/test_shard_map.py checks on the CPU)
+static bool shard_args_ok(int n_shards, int block_rows) {
+    return n_shards >= 1 && n_shards <= yrb::XS_MAX_SHARDS && block_rows >= 64 && (block_rows & (block_rows - 1)) == 0;
+}
+int yrb_shard_locate(int n_shards, int block_rows, int64_t global_row, int* out_shard, int64_t* out_local) {
+    if (!shard_args_ok(n_shards, block_rows) || global_row < 0 || !out_shard || !out_local) return fail(YRB_ERR_INVALID, "bad shard map arguments");
+    const int64_t b = global_row / block_rows;
+    *out_shard = (int)(b % n_shards);
+    *out_local = (b / n_shards) * block_rows + global_row % block_rows;
+    return YRB_OK;
+}
+int yrb_shard_global(int n_shards, int block_rows, int shard, int64_t local_row, int64_t* out_global) {
+    if (!shard_args_ok(n_shards, block_rows) || shard < 0 || shard >= n_shards || local_row < 0 || !out_global)
+        return fail(YRB_ERR_INVALID, "bad shard map arguments");
+    int shift = 0;
+    while ((1 << shift) < block_rows) ++shift;
+    *out_global = yrb::xs_global_row(n_shards, shift, shard, (uint32_t)local_row);   // the function the merge kernels use
+    return YRB_OK;
+}
+int yrb_shard_rows(int n_shards, int block_rows, int64_t total_rows, int shard, int64_t* out_rows) {
+    if (!shard_args_ok(n_shards, block_rows) || shard < 0 || shard >= n_shards || total_rows < 0 || !out_rows)
+        return fail(YRB_ERR_INVALID, "bad shard map arguments");
+    const int64_t nb = total_rows / block_rows, rem = total_rows % block_rows;
+    int64_t r = (nb / n_shards + (shard < nb % n_shards ? 1 : 0)) * block_rows;
+    if (shard == nb % n_shards) r += rem;
+    *out_rows = r;
+    return YRB_OK;
+}
 
 int yrb_sharded_create(yrb_sharded** out, const int* devices, int n_devices, int dim, int metric, int storage_dtype,
                        int64_t reserve_rows, int block_rows_arg) {

@@ -36,7 +36,7 @@ EXPORTS = (
     "yrb_merge_topk_device", "yrb_exchange_handle_bytes", "yrb_exchange_last_error", "yrb_exchange_create",
     "yrb_exchange_connect", "yrb_exchange_merge", "yrb_exchange_search", "yrb_exchange_destroy", "yrb_index_set_path", "yrb_index_set_reserved_sms", "yrb_index_stats", "yrb_index_profile",
     "yrb_index_profile_read", "yrb_index_cache_stats",
-    "yrb_sharded_create", "yrb_sharded_destroy", "yrb_sharded_count", "yrb_sharded_info", "yrb_sharded_shard",
+    "yrb_shard_locate", "yrb_shard_global", "yrb_shard_rows", "yrb_sharded_create", "yrb_sharded_destroy", "yrb_sharded_count", "yrb_sharded_info", "yrb_sharded_shard",
     "yrb_sharded_append_host_f32", "yrb_sharded_append_device_f32", "yrb_sharded_read_rows", "yrb_sharded_read_raw",
     "yrb_sharded_append_raw", "yrb_sharded_set_live", "yrb_sharded_truncate", "yrb_sharded_clear",
     "yrb_sharded_column_write", "yrb_sharded_where", "yrb_sharded_search", "yrb_sharded_search_multi", "yrb_sharded_search_ex", "yrb_sharded_stats",
@@ -116,6 +116,9 @@ def lib() -> C.CDLL:
     L.yrb_index_profile.argtypes = [vp, i32]
     L.yrb_index_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.yrb_index_cache_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.yrb_shard_locate.argtypes = [i32, i32, i64, C.POINTER(i32), C.POINTER(i64)]
+    L.yrb_shard_global.argtypes = [i32, i32, i32, i64, C.POINTER(i64)]
+    L.yrb_shard_rows.argtypes = [i32, i32, i64, i32, C.POINTER(i64)]
     L.yrb_sharded_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, i32, i32, i64, i32]
     L.yrb_sharded_destroy.argtypes = [vp]
     L.yrb_sharded_count.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
@@ -460,6 +463,24 @@ class ShardedIndex(Index):
         raise NativeError(-4, "a sharded index answers through host buffers (the merged result lands in pinned host memory)")
 
     search_device_ids = search_device
+
+
+def shard_locate(n_shards: int, block_rows: int, global_row: int) -> tuple[int, int]:
+    s, l = C.c_int(), C.c_int64()
+    _ck(lib().yrb_shard_locate(n_shards, block_rows, global_row, C.byref(s), C.byref(l)))
+    return s.value, l.value
+
+
+def shard_global(n_shards: int, block_rows: int, shard: int, local_row: int) -> int:
+    g = C.c_int64()
+    _ck(lib().yrb_shard_global(n_shards, block_rows, shard, local_row, C.byref(g)))
+    return g.value
+
+
+def shard_rows(n_shards: int, block_rows: int, total_rows: int, shard: int) -> int:
+    r = C.c_int64()
+    _ck(lib().yrb_shard_rows(n_shards, block_rows, total_rows, shard, C.byref(r)))
+    return r.value
 
 
 def merge_topk_device(device: int, dev_keys: int, parts: int, nq: int, k: int, dev_row_base: int, dev_ids: int,
