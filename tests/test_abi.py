@@ -56,3 +56,28 @@ def test_decode_keys_inverse_of_oracle_key():
     keys = (ox.score_key_u32(s).astype(np.uint64) << np.uint64(32)) | (~rows).astype(np.uint64)
     r, sc = native.decode_keys(np.concatenate([keys, np.zeros(1, np.uint64)]))
     assert np.array_equal(r[:-1], rows) and np.array_equal(sc[:-1], s) and r[-1] == -1 and sc[-1] == -np.inf
+
+
+def _run_c_consumer(tmp_path):
+    import subprocess
+
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "abi_smoke"
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(root / "include"),
+           str(root / "tests" / "abi_c" / "abi_smoke.c"), "-o", str(exe), str(native.LIB_PATH), f"-Wl,-rpath,{native.LIB_PATH.parent}"]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    assert b.returncode == 0, b.stdout + b.stderr
+    return subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+
+
+def test_header_is_plain_c_and_a_c_program_links_every_entry(tmp_path):
+    """include/yrb200.h through a C11 compiler with -pedantic -Werror, linked against libyrb200.so from C.  Without a
+    B200 the program checks that constructors refuse to work (no CPU fallback) and that the stateless row map answers."""
+    r = _run_c_consumer(tmp_path)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_consumer_searches_on_the_device(tmp_path):
+    r = _run_c_consumer(tmp_path)
+    assert r.returncode == 0 and r.stdout.startswith("OK device"), r.stdout + r.stderr
