@@ -266,3 +266,29 @@ def test_k1q_fewer_passing_rows_than_k():
     ids, scores, counts = ix.search(unit_rows(6, d, 46), 10, mask=ox.pack_mask(mask))
     assert counts.tolist() == [3] * 6
     assert all(sorted(ids[j, :3].tolist()) == [3, 77, 4999] and (ids[j, 3:] == -1).all() for j in range(6))
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_batches_beyond_256_queries_sweep_the_corpus_once(metric):
+    """More than 256 queries run as ONE launch of the pair kernel over up to four 256-query chunks per row tile (C5's
+    shape): 300 / 700 / 1024 / 1300 queries (partial last chunks, a second launch), k = 10 and 100,
+    with a shared bitmask, against the oracle — and bit-identical to the same batch issued as 256-query chunks."""
+    n, d = 60_000, 192
+    x = unit_rows(n, d, 61)
+    ix = native.Index(d, metric, "bf16", 0, n)
+    ix.append(x)
+    rows = ix.read_rows(np.arange(n))
+    m = np.random.default_rng(8).random(n) < 0.5
+    l0 = ix.launches()
+    for nq in (300, 700, 1024, 1300):
+        q = unit_rows(nq, d, 62 + nq)
+        for k, mask in ((10, None), (100, None), (10, m)):
+            ids, scores, counts = ix.search(q, k, mask=None if mask is None else ox.pack_mask(mask))
+            assert (counts == k).all()
+            for j in sorted({0, 127, 128, 255, 256, 299, nq // 2, nq - 1}):
+                check_topk(ids[j], scores[j], rows, ox.prepare(q[j], metric, "bf16")[0], k, metric, "bf16", mask)
+            parts = [ix.search(q[a:a + 256], k, mask=None if mask is None else ox.pack_mask(mask)) for a in range(0, nq, 256)]
+            np.testing.assert_array_equal(ids, np.concatenate([p[0] for p in parts]))
+            np.testing.assert_array_equal(scores.view(np.uint32), np.concatenate([p[1] for p in parts]).view(np.uint32))
+    assert ix.launches() > l0
+    ix.close()

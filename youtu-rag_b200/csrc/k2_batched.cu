@@ -243,9 +243,9 @@ __device__ __forceinline__ void
                     else epi_append(v, mw, thr, r0, buf_keys, cnt);
                 }
                 if (pass == 0)
-                    thr = fmaxf(score_floor, epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, (int)gridDim.x, 1, k, nq, qi,
+                    thr = fmaxf(score_floor, epi_exchange_thresholds(tops_l, tops, m_tops, thr_out, sync_ctr, (int)gridDim.x, 1, k, qi,
                                                                      active, (int)blockIdx.x * 4 * QB + ew, (int)gridDim.x * 4 * QB,
-                                                                     128 * QB, threadIdx.x == 128, lane));
+                                                                     128 * QB, threadIdx.x == 128, lane, 0, nq));
             }
             tc_fence_before();
             __syncwarp();
@@ -323,6 +323,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct K2State {
     EncodeTiledFn encode = nullptr;
     int slots = 0;
+    int qcap = 0;   // query slots per CTA row of the candidate buffers: MAX_Q, or MAX_Q * MAX_QC once a batch of more than 256 queries was seen
     uint64_t* cand_keys = nullptr;
     int* cand_cnt = nullptr;
     float* tops = nullptr;
@@ -433,17 +434,30 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
         s->encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     const int want_slots = sm_count + 16;  // grids are rounded up to the cluster size
-    if (s->slots < want_slots) {
+    // batches of more than 256 queries run the pair kernel over up to MAX_QC chunks per launch (one pass over the corpus):
+    // the candidate buffers then hold MAX_Q * MAX_QC query slots per CTA (344 MB per device instead of 86 MB)
+    static int fuse_env = -1;
+    if (fuse_env < 0) fuse_env = getenv("YRB_K2_FUSE") ? atoi(getenv("YRB_K2_FUSE")) : 1;
+    static int multi_env = -1;
+    if (multi_env < 0) multi_env = getenv("YRB_K2_MULTICHUNK") ? atoi(getenv("YRB_K2_MULTICHUNK")) : 1;
+    static bool fuse_ok[2] = {true, true};  // [0] one-CTA kernel, [1] pair kernel: cleared if a cooperative launch is refused
+    const bool multichunk = nq > k2::MAX_Q && !rowmap && multi_env != 0 && fuse_env != 0 && fuse_ok[1] && k2_use_pair(force_pair);
+    const int want_qcap = multichunk ? k2::MAX_Q * k2::MAX_QC : k2::MAX_Q;
+    if (s->slots < want_slots || s->qcap < want_qcap) {
+        const int slots = std::max(want_slots, s->slots), qcap = std::max(want_qcap, s->qcap);
+        K2CK(cudaStreamSynchronize(st));
         if (s->cand_keys) cudaFree(s->cand_keys);
         if (s->cand_cnt) cudaFree(s->cand_cnt);
         if (s->tops) cudaFree(s->tops);
         if (s->thr0) cudaFree(s->thr0);
         s->cand_keys = nullptr; s->cand_cnt = nullptr; s->tops = nullptr; s->thr0 = nullptr;
-        K2CK(cudaMalloc(&s->cand_keys, (size_t)want_slots * k2::MAX_Q * k2::CAP * 8));
-        K2CK(cudaMalloc(&s->cand_cnt, ((size_t)want_slots * k2::MAX_Q + 1) * 4));  // + the grid-barrier counter
-        K2CK(cudaMalloc(&s->tops, (size_t)want_slots * k2::MAX_TOPS * k2::MAX_Q * 4));
-        K2CK(cudaMalloc(&s->thr0, (size_t)k2::MAX_Q * 4));
-        s->slots = want_slots;
+        s->slots = s->qcap = 0;
+        K2CK(cudaMalloc(&s->cand_keys, (size_t)slots * qcap * k2::CAP * 8));
+        K2CK(cudaMalloc(&s->cand_cnt, ((size_t)slots * qcap + 1) * 4));  // + the grid-barrier counter
+        K2CK(cudaMalloc(&s->tops, (size_t)slots * k2::MAX_TOPS * qcap * 4));
+        K2CK(cudaMalloc(&s->thr0, (size_t)qcap * 4));
+        s->slots = slots;
+        s->qcap = qcap;
     }
     const int kblocks = ld / k2::BLOCK_K;
     const int tiles = (int)((n_rows + k2::BLOCK_R - 1) / k2::BLOCK_R);
@@ -457,14 +471,15 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
 
     // sampling inside the main launch (cooperative) unless YRB_K2_FUSE=0 (the round-1 sequence: sampling launch,
     // threshold kernel, main launch — kept for A/B runs)
-    static int fuse_env = -1;
-    if (fuse_env < 0) fuse_env = getenv("YRB_K2_FUSE") ? atoi(getenv("YRB_K2_FUSE")) : 1;
-    static bool fuse_ok[2] = {true, true};  // [0] one-CTA kernel, [1] pair kernel: cleared if a cooperative launch is refused
-    unsigned int* sync_ctr = reinterpret_cast<unsigned int*>(s->cand_cnt + (size_t)s->slots * k2::MAX_Q);  // zeroed with the counts
-    for (int c0 = 0; c0 < nq; c0 += k2::MAX_Q) {
+    unsigned int* sync_ctr = reinterpret_cast<unsigned int*>(s->cand_cnt + (size_t)s->slots * s->qcap);  // zeroed with the counts
+    int step_q = k2::MAX_Q;
+    for (int c0 = 0; c0 < nq; c0 += step_q) {
         const bool use_pair_now = (nq - c0 > k2::BLOCK_Q) && !rowmap && k2_use_pair(force_pair);
         const bool fuse = fuse_env != 0 && fuse_ok[use_pair_now ? 1 : 0];
-        const int nqc = nq - c0 < k2::MAX_Q ? nq - c0 : k2::MAX_Q;
+        // queries of this launch: up to MAX_QC chunks on the pair kernel with fused sampling, one chunk otherwise
+        const int chunks = (use_pair_now && fuse && multichunk) ? std::min(k2::MAX_QC, (nq - c0 + k2::MAX_Q - 1) / k2::MAX_Q) : 1;
+        step_q = chunks * k2::MAX_Q;
+        const int nqc = nq - c0 < step_q ? nq - c0 : step_q;
         const int QB = nqc > k2::BLOCK_Q ? 2 : 1;
         const float* qn = metric == YRB_METRIC_L2 ? q_sqnorm + c0 : nullptr;
         const uint32_t* mask = mask_all ? mask_all + (size_t)c0 * mask_q_stride : nullptr;
@@ -479,7 +494,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             xs_c.q0 += c0;
             xs = &xs_c;
         }
-        K2CK(cudaMemsetAsync(s->cand_cnt, 0, ((size_t)s->slots * k2::MAX_Q + 1) * 4, st));
+        K2CK(cudaMemsetAsync(s->cand_cnt, 0, ((size_t)s->slots * s->qcap + 1) * 4, st));
         if (nqc > k2::BLOCK_Q && !rowmap && k2_use_pair(force_pair)) {
             // CTA pairs (cta_group::2): 256-row tiles, CTA r of a pair owns queries [128r, 128r+128)
             const int tiles2 = (int)((n_rows + 255) / 256);
@@ -487,6 +502,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             if (tiles2 < n_pairs) n_pairs = tiles2;
             const int grid2 = 2 * n_pairs;
             const int iters2 = (tiles2 + n_pairs - 1) / n_pairs;
+            const int q_stride2 = chunks > 1 ? s->qcap : k2::MAX_Q;   // single chunks keep the 256-slot rows (round-1 layout)
             CUtensorMap mq2;
             if (!make_map(s, &mq2, reinterpret_cast<const char*>(q) + (size_t)c0 * ld * 2, (uint64_t)((nqc + 127) / 128 * 128), ld,
                           k2::BLOCK_Q, err))
@@ -498,7 +514,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             const float* thr2 = nullptr;
             if (sampled2 && !fuse) {
                 K2CK(launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, 1, nqc, k, mask, mask_q_stride, nullptr, s->cand_keys,
-                                      s->cand_cnt, s->tops, m_tops2, qn, xn, nullptr, nullptr, score_floor, st));
+                                      s->cand_cnt, s->tops, m_tops2, qn, xn, nullptr, nullptr, score_floor, 1, k2::MAX_Q, st));
                 k2::k2_threshold_kernel<<<(nqc + 7) / 8, 256, 0, st>>>(s->tops, n_pairs, m_tops2, k, s->thr0, 2, nqc);
                 K2CK(cudaGetLastError());
                 *launches += 2;
@@ -509,19 +525,19 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
             {
                 cudaError_t e = launch_gemm_pair(grid2, mq2, mr, n_rows, kblocks, iters2, nqc, k, mask, mask_q_stride, thr2, s->cand_keys,
                                                  s->cand_cnt, fz ? s->tops : nullptr, fz ? m_tops2 : 0, qn, xn, fz ? s->thr0 : nullptr,
-                                                 fz ? sync_ctr : nullptr, score_floor, st);
+                                                 fz ? sync_ctr : nullptr, score_floor, chunks, q_stride2, st);
                 if (e != cudaSuccess && fz) {  // cooperative launch refused: redo this chunk with the separate sampling pass
                     fprintf(stderr, "yrb200: cooperative launch of k2_gemm_topk_pair refused (%s); sampling runs as separate launches\n",
                             cudaGetErrorString(e));
                     cudaGetLastError();
                     fuse_ok[1] = false;
-                    c0 -= k2::MAX_Q;
+                    step_q = 0;   // redo from the same c0 (as single chunks with the separate sampling pass)
                     continue;
                 }
                 K2CK(e);
             }
             if (ev_start && c0 == 0) K2CK(cudaEventRecord(ev_stop, st));
-            K2CK(launch_select_segments(s->cand_keys, (int64_t)k2::MAX_Q * k2::CAP, k2::CAP, s->cand_cnt, k2::MAX_Q, 1, grid2, 0,
+            K2CK(launch_select_segments(s->cand_keys, (int64_t)q_stride2 * k2::CAP, k2::CAP, s->cand_cnt, q_stride2, 1, grid2, 0,
                                         k2::CAP, nullptr, nqc, k, o_keys, st, o_ids, o_scores, o_counts, xs));
             *launches += 2;
             continue;
@@ -562,7 +578,7 @@ int k2_search(K2State* s, const void* rows, int64_t n_rows, int64_t capacity, in
                         cudaGetErrorString(e));
                 cudaGetLastError();
                 fuse_ok[0] = false;
-                c0 -= k2::MAX_Q;
+                step_q = 0;
                 continue;
             }
             K2CK(e);

@@ -33,5 +33,5 @@ namespace yrb {
 cudaError_t launch_gemm_pair(int grid, const CUtensorMap& mq, const CUtensorMap& mr, int64_t n_rows, int kblocks, int iters,
                              int nq, int k, const uint32_t* mask, int64_t mask_q_stride, const float* thr, uint64_t* ck,
                              int* cc, float* tops, int m_tops, const float* q_sqnorm, const float* row_sqnorm,
-                             float* thr_out, unsigned int* sync_ctr, float score_floor, cudaStream_t st);
+                             float* thr_out, unsigned int* sync_ctr, float score_floor, int nqc, int q_stride, cudaStream_t st);
 }  // namespace yrb

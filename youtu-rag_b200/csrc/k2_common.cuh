@@ -15,7 +15,8 @@ constexpr int BLOCK_R = 128;   // MMA N: corpus rows per tile (256 measured slow
 constexpr int BLOCK_K = 64;    // bf16 elements per k-block = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int CAP = 256;       // candidate slots per (CTA, query)
-constexpr int MAX_Q = 256;     // queries per launch (2 query blocks)
+constexpr int MAX_Q = 256;     // queries per chunk (2 query blocks): one accumulator set
+constexpr int MAX_QC = 4;      // chunks the pair kernel sweeps per row tile: up to 1024 queries read the corpus ONCE
 constexpr int QTILE_BYTES = BLOCK_Q * BLOCK_K * 2;  // 16 KiB: one query block x one k-block
 constexpr int RTILE_BYTES = BLOCK_R * BLOCK_K * 2;  // 16 KiB: one row tile x one k-block
 constexpr int MAX_TOPS = 4;   // best scores each (CTA, query) publishes in the sampling pass
@@ -276,7 +277,9 @@ __device__ __forceinline__ void epi_grid_barrier(unsigned int* ctr, unsigned int
 // `s > thr`): every published score belongs to a distinct real row, so at least k rows reach it and it cannot exceed
 // the true k-th best.  Fewer than k published → -inf.  cta_stride 1: every CTA published for q; 2 (pair kernel):
 // CTA 2i + (q >= 128).  Bisection on the monotone bit patterns (32 rounds of compare + warp popcount); whole warp.
-__device__ __forceinline__ float warp_threshold(const float* tops, int n_cta, int m, int k, int q, int cta_stride, int lane) {
+// q_stride: query slots per CTA row of `tops` (MAX_Q, or MAX_Q * chunks for the pair kernel's multi-chunk launches).
+__device__ __forceinline__ float warp_threshold(const float* tops, int n_cta, int m, int k, int q, int cta_stride, int lane,
+                                                int q_stride = MAX_Q) {
     constexpr int NV = (148 + 16) * MAX_TOPS / 32 + 1;  // n <= (SMs + cluster padding) * MAX_TOPS
     const int n = n_cta * m;
     uint32_t v[NV];
@@ -285,8 +288,8 @@ __device__ __forceinline__ float warp_threshold(const float* tops, int n_cta, in
         const int i = lane + 32 * j;
         float f = -INFINITY;
         if (i < n) {
-            const int cta = (i / m) * cta_stride + (cta_stride == 2 && q >= BLOCK_Q ? 1 : 0);
-            f = __ldcg(tops + ((int64_t)cta * MAX_TOPS + (i % m)) * MAX_Q + q);
+            const int cta = (i / m) * cta_stride + (cta_stride == 2 && (q % MAX_Q) >= BLOCK_Q ? 1 : 0);
+            f = __ldcg(tops + ((int64_t)cta * MAX_TOPS + (i % m)) * q_stride + q);
         }
         v[j] = score_bits(f);
     }
@@ -303,22 +306,24 @@ __device__ __forceinline__ float warp_threshold(const float* tops, int n_cta, in
     }
     return (n >= k) ? nextafterf(bits_score(t), -INFINITY) : -INFINITY;
 }
-// steps (b)-(d) above.  epi_warp / n_epi_warps number the epilogue warps of the whole grid.
+// steps (b)-(d) above.  epi_warp / n_epi_warps number the epilogue warps of the whole grid.  One call handles the
+// queries [q_begin, q_end) (a chunk); `round` counts the calls of this launch (the counter only grows).
 __device__ __forceinline__ float epi_exchange_thresholds(const float (&tops_l)[MAX_TOPS], float* tops, int m_tops, float* thr_out,
-                                                         unsigned int* sync_ctr, int n_cta_pub, int cta_stride, int k, int nq,
-                                                         int qi, bool active, int epi_warp, int n_epi_warps, int n_epi_threads,
-                                                         bool first_thread, int lane) {
+                                                         unsigned int* sync_ctr, int n_cta_pub, int cta_stride, int k, int qi,
+                                                         bool active, int epi_warp, int n_epi_warps, int n_epi_threads,
+                                                         bool first_thread, int lane, int q_begin, int q_end,
+                                                         int q_stride = MAX_Q, int round = 0) {
     if (active) {
 #pragma unroll
         for (int i = 0; i < MAX_TOPS; ++i)
-            if (i < m_tops) tops[((int64_t)blockIdx.x * MAX_TOPS + i) * MAX_Q + qi] = tops_l[i];
+            if (i < m_tops) tops[((int64_t)blockIdx.x * MAX_TOPS + i) * q_stride + qi] = tops_l[i];
     }
-    epi_grid_barrier(sync_ctr, gridDim.x, n_epi_threads, first_thread);
-    for (int q = epi_warp; q < nq; q += n_epi_warps) {
-        const float t = warp_threshold(tops, n_cta_pub, m_tops, k, q, cta_stride, lane);
+    epi_grid_barrier(sync_ctr, (2u * round + 1u) * gridDim.x, n_epi_threads, first_thread);
+    for (int q = q_begin + epi_warp; q < q_end; q += n_epi_warps) {
+        const float t = warp_threshold(tops, n_cta_pub, m_tops, k, q, cta_stride, lane, q_stride);
         if (lane == 0) thr_out[q] = t;
     }
-    epi_grid_barrier(sync_ctr, 2u * gridDim.x, n_epi_threads, first_thread);
+    epi_grid_barrier(sync_ctr, (2u * round + 2u) * gridDim.x, n_epi_threads, first_thread);
     return active ? __ldcg(thr_out + qi) : INFINITY;
 }
 
