@@ -13,6 +13,8 @@ kernel over NVLink peer memory; `--exchange nccl` = all-gather + merge kernel).
 The same JSON line carries, under `also`, short runs of the other BASELINE.json configurations on the same box:
   c4     10M x 1024 + 10 % metadata mask, single query (configs[3]; every N)
   t10mb  10M x 1024, 256-query batches, top-100 (the batched scaling case of north_star; every N)
+  t10mq  10M x 1024, 1024-query batches, top-10 (C5's batch shape on the resident corpus: ONE K2 launch sweeps four
+         256-query chunks per row tile, the corpus is read once; every N)
   c3     1M x 1024, 256-query batch, top-100 (configs[2]; N = 1 only — a one-GPU configuration)
   sharded_store  (N > 1, rank 0) the drop-in store's in-process form: ONE process driving all N GPUs through
          `yrb_sharded_search` (host buffers in, merged result in pinned host memory out)
@@ -69,6 +71,7 @@ WORKLOADS = {
     "t10mb": (10_000_000, 1024, 256, 100, None),     # 256-query batches over the 10M corpus (batched scaling case)
     "c3s": (125_000, 1024, 256, 100, None),          # one C3 shard of an 8-GPU run, for the fixed-cost breakdown
     "t10mbs": (1_250_000, 1024, 256, 100, None),     # one t10mb shard of an 8-GPU run
+    "t10mq": (10_000_000, 1024, 1024, 10, None),     # 1024-query batches over the 10M corpus (C5's batch shape: one K2 launch, one corpus pass)
 }
 DEFAULT_WORKLOAD = "t10m"
 N_QUERY_SETS = 64
@@ -639,7 +642,7 @@ def run_b200(args):
     default_run = args.workload is None and not args.no_also
     if default_run:
         # the other BASELINE.json configurations on the same resident corpus (short runs)
-        for name, st in (("c4", max(20, args.steps // 2)), ("t10mb", max(5, args.steps // 10))):
+        for name, st in (("c4", max(20, args.steps // 2)), ("t10mb", max(5, args.steps // 10)), ("t10mq", max(3, args.steps // 25))):
             r, p = measure(env, corpus, searcher, name, st, max(3, args.warmup // 4), args, with_cpu=False)
             also[name] = {x: r[x] for x in ALSO_KEYS}
             probes.append(p)
