@@ -643,7 +643,13 @@ def run_b200(args):
     if default_run:
         # the other BASELINE.json configurations on the same resident corpus (short runs)
         for name, st in (("c4", max(20, args.steps // 2)), ("t10mb", max(5, args.steps // 10)), ("t10mq", max(3, args.steps // 25))):
-            r, p = measure(env, corpus, searcher, name, st, max(3, args.warmup // 4), args, with_cpu=False)
+            try:
+                r, p = measure(env, corpus, searcher, name, st, max(3, args.warmup // 4), args, with_cpu=False)
+            except Exception as e:  # noqa: BLE001 - a side leg must not take the main line with it (one process: no peers to desynchronise)
+                if env.world > 1:
+                    raise
+                also[name] = {"error": f"{type(e).__name__}: {e}"}
+                continue
             also[name] = {x: r[x] for x in ALSO_KEYS}
             probes.append(p)
     rep = None
