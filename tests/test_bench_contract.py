@@ -22,3 +22,21 @@ def test_reference_arm_prints_the_contract_line():
     cb = j["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": j["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_traffic_ratios_cover_every_kernel_variant_the_bench_reports():
+    """bench.py's `roofline.traffic` = ratio x this run's algorithmic bytes; every ratio comes from a committed
+    `ncu --set full` summary and must name it (profiles/traffic.json)."""
+    root = Path(__file__).resolve().parent.parent
+    t = json.loads((root / "profiles" / "traffic.json").read_text())
+    for key in ("k1", "k2", "k2mc"):
+        assert 1.0 <= t[key]["ratio"] < 1.1, key            # no re-reads: dram bytes within 10 % of the algorithmic bytes
+        src = t[key]["source"].split(":")[0]
+        assert (root / src).exists(), src
+    sys.path.insert(0, str(root))
+    try:
+        import bench
+    finally:
+        sys.path.pop(0)
+    assert bench.traffic_of("k2mc", 1e9, None)["traffic"] == t["k2mc"]["ratio"] * 1e9
+    assert bench.traffic_of("k2mc", 1e9, True) == {"traffic": None}   # no capture of a masked multi-chunk launch
